@@ -1,0 +1,104 @@
+// common.cuh -- shared helpers for libgcrl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+#include "../../include/gcrl_b200.h"
+
+#define HID GCRL_HID
+
+namespace gcrl {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+#define GCRL_CHECK_ARG(cond)                                                          \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            gcrl::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond); \
+            return GCRL_ERR_INVALID;                                                  \
+        }                                                                             \
+    } while (0)
+
+#define GCRL_CUDA(call)                                                               \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            gcrl::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,               \
+                            cudaGetErrorString(e_));                                  \
+            return GCRL_ERR_CUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+#define GCRL_LAUNCH_CHECK() GCRL_CUDA(cudaGetLastError())
+
+// ---- flat parameter layout (state_dict order, architecture.py:157-167) -----------------
+struct BlockW {
+    const float* W1;  // [64, 2*Dv + De]  message_mlp.0.weight
+    const float* b1;  // [64]
+    const float* W2;  // [64, 64]         message_mlp.2.weight
+    const float* b2;  // [64]
+    const float* U1;  // [64, 256 + Dv]   update_mlp.0.weight
+    const float* c1;  // [64]
+    const float* U2;  // [64, 64]         update_mlp.2.weight
+    const float* c2;  // [64]
+    int Dv, De;
+};
+struct HeadW {
+    const float *F1, *f1, *F2, *f2, *F3, *f3;
+    int Dg;
+};
+struct NetW {
+    BlockW blk[GCRL_N_BLOCKS];
+    HeadW head;
+    int64_t total;
+};
+
+inline NetW make_net(const float* p, int vdim, int edim, int gdim) {
+    NetW n;
+    int64_t o = 0;
+    int dv = vdim, de = edim;
+    for (int l = 0; l < GCRL_N_BLOCKS; ++l) {
+        BlockW& b = n.blk[l];
+        b.Dv = dv; b.De = de;
+        b.W1 = p + o; o += (int64_t)HID * (2 * dv + de);
+        b.b1 = p + o; o += HID;
+        b.W2 = p + o; o += HID * HID;
+        b.b2 = p + o; o += HID;
+        b.U1 = p + o; o += (int64_t)HID * (4 * HID + dv);
+        b.c1 = p + o; o += HID;
+        b.U2 = p + o; o += HID * HID;
+        b.c2 = p + o; o += HID;
+        dv = HID; de = HID;
+    }
+    n.head.Dg = gdim;
+    n.head.F1 = p + o; o += (int64_t)HID * (HID + gdim);
+    n.head.f1 = p + o; o += HID;
+    n.head.F2 = p + o; o += HID * HID;
+    n.head.f2 = p + o; o += HID;
+    n.head.F3 = p + o; o += HID;
+    n.head.f3 = p + o; o += 1;
+    n.total = o;
+    return n;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// bump allocator over a caller-provided workspace
+struct Arena {
+    char* base; size_t size; size_t used;
+    Arena(void* b, size_t s) : base((char*)b), size(s), used(0) {}
+    template <typename T> T* take(size_t n) {
+        size_t bytes = align_up(n * sizeof(T));
+        T* p = (T*)(base + used);
+        used += bytes;
+        return p;
+    }
+    bool ok() const { return used <= size; }
+};
+
+#define PNA_EPS 1e-5f  // principal_neighbourhood_aggregation.py:64
+
+}  // namespace gcrl

@@ -1,0 +1,602 @@
+// gn_forward.cu -- GN Q-network forward (architecture.py:179-199), fp32 parity path.
+//
+// Per GNNBlock (architecture.py:80-99) the reference runs gather -> cat -> Linear -> ReLU ->
+// Linear over E edge rows, five torch_scatter reductions and a per-vertex MLP.  Here:
+//   * the first message Linear is split algebraically,
+//       W1 [x_i | x_j | e] + b1 = (A x_i + b1) + B x_j + C e ,
+//     so the vertex-side projections Pi = A h + b1, Pj = B h are computed once per vertex
+//     (fused into the previous block's vertex kernel) and the per-edge work is two 64x64
+//     mat-vecs; no [E,192] concat is ever materialised;
+//   * k_edge_fwd fuses message MLP + PNA aggregation: one pass reads e_{l-1}, writes e_l
+//     (skipped for block 5, whose edge output the network discards, :187) and emits
+//     mean|min|max|std per destination vertex through the CTA-level segmented reducer;
+//   * k_node_update fuses update MLP (+ next block's Pi/Pj, or the fc1/fc2/fc3 head).
+//
+// Work decomposition of k_edge_fwd: work item w owns the destination vertices whose segment
+// starts in [w*ITEM_EDGES, (w+1)*ITEM_EDGES) -- whole segments, found by binary search on
+// seg_off, so no cross-CTA combination and no atomics.  Persistent CTAs stride over items.
+#include "segreduce.cuh"
+
+namespace gcrl {
+
+constexpr int TILE = 128;         // edge rows per tile
+constexpr int LDT = 68;           // padded smem row stride (floats), keeps 16 B alignment
+constexpr int ITEM_EDGES = 2048;  // target edges per work item
+
+struct EdgeSmem {
+    float Wa[64][64];  // Wa[k][o] = W1[o][2Dv + k]  (edge part of message_mlp.0, transposed)
+    float Wb[64][64];  // Wb[k][o] = W2[o][k]        (message_mlp.2, transposed)
+    float A[TILE][LDT];  // e_{l-1} tile; reused for the output message tile
+    union {
+        float H[TILE][LDT];  // hidden activations
+        RedScratch red;      // reducer partials (H is dead by then)
+    };
+    float b2[64];
+    int32_t dst[TILE];
+    int32_t src[TILE];
+};
+
+struct EdgeArgs {
+    const float* Pi;      // [N,64]  A h + b1
+    const float* Pj;      // [N,64]  B h
+    const float* e_prev;  // [E,De]  internal order
+    int De;               // 64 for blocks 2-5, edge_dim for block 1
+    const float* W1;      // message_mlp.0.weight [64, ldW1]
+    int ldW1, coff;       // coff = 2*Dv: first column of the edge part
+    const float* W2;      // [64,64]
+    const float* b2;      // [64]
+    const int32_t* seg_off;
+    const int32_t* src;
+    const int32_t* dst;
+    int32_t N;
+    int32_t E;
+    float* m_out;         // [E,64] or null
+    AggOut out;
+};
+
+// acc[8][4] += A[8rg+i][:] . W[:][4cg+j], K = 64
+__device__ __forceinline__ void gemm64(const float (*A)[LDT], const float (*W)[64], int rg, int cg,
+                                       float acc[8][4]) {
+#pragma unroll 2
+    for (int k4 = 0; k4 < 16; ++k4) {
+        float4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&A[8 * rg + i][4 * k4]);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4 w = *reinterpret_cast<const float4*>(&W[4 * k4 + kk][4 * cg]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                acc[i][0] = fmaf(av, w.x, acc[i][0]);
+                acc[i][1] = fmaf(av, w.y, acc[i][1]);
+                acc[i][2] = fmaf(av, w.z, acc[i][2]);
+                acc[i][3] = fmaf(av, w.w, acc[i][3]);
+            }
+        }
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256, 2) k_edge_fwd(const EdgeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EdgeSmem& S = *reinterpret_cast<EdgeSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int cg = tid & 15, rg = tid >> 4;
+
+    // weights -> smem (transposed); one-time per CTA
+    for (int t = tid; t < 64 * 64; t += 256) {
+        int o = t & 63, k = t >> 6;
+        S.Wb[k][o] = a.W2[o * 64 + k];
+        if (!FIRST) S.Wa[k][o] = a.W1[o * a.ldW1 + a.coff + k];
+        else if (k < a.De) S.Wa[k][o] = a.W1[o * a.ldW1 + a.coff + k];
+    }
+    if (tid < 64) S.b2[tid] = a.b2[tid];
+    __syncthreads();
+
+    const int64_t n_items = ((int64_t)a.E + ITEM_EDGES - 1) / ITEM_EDGES;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const int32_t v0 = seg_lower_bound(a.seg_off, a.N, w * ITEM_EDGES);
+        const int32_t v1 = (w + 1 == n_items) ? a.N : seg_lower_bound(a.seg_off, a.N, (w + 1) * ITEM_EDGES);
+        const int32_t e0 = a.seg_off[v0], e1 = a.seg_off[v1];
+        Carry carry;
+        carry.dst = -1;
+        stat_init(carry.s);
+        for (int32_t t0 = e0; t0 < e1; t0 += TILE) {
+            const int nrows = min(TILE, e1 - t0);
+            if (tid < TILE) {
+                const bool ok = tid < nrows;
+                S.dst[tid] = ok ? a.dst[t0 + tid] : -1;
+                S.src[tid] = ok ? a.src[t0 + tid] : 0;
+            }
+            if (!FIRST) {
+                // e_{l-1} tile: 128 rows x 256 B contiguous in HBM -> coalesced 128-bit loads
+                const float4* g = reinterpret_cast<const float4*>(a.e_prev + (int64_t)t0 * 64);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int idx = it * 256 + tid;
+                    int r = idx >> 4, c4 = idx & 15;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nrows) v = __ldcs(g + idx);
+                    *reinterpret_cast<float4*>(&S.A[r][4 * c4]) = v;
+                }
+            } else {
+                for (int t = tid; t < TILE * a.De; t += 256) {
+                    int r = t / a.De, d = t - r * a.De;
+                    S.A[r][d] = (r < nrows) ? a.e_prev[(int64_t)(t0 + r) * a.De + d] : 0.f;
+                }
+            }
+            __syncthreads();
+
+            // ---- z1 = Pi[dst] + Pj[src] + C e ; hidden = relu(z1) ------------------------
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+            if (!FIRST) {
+                gemm64(S.A, S.Wa, rg, cg, acc);
+            } else {
+                for (int d = 0; d < a.De; ++d) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&S.Wa[d][4 * cg]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float ev = S.A[8 * rg + i][d];
+                        acc[i][0] = fmaf(ev, wv.x, acc[i][0]);
+                        acc[i][1] = fmaf(ev, wv.y, acc[i][1]);
+                        acc[i][2] = fmaf(ev, wv.z, acc[i][2]);
+                        acc[i][3] = fmaf(ev, wv.w, acc[i][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 8 * rg + i;
+                float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < nrows) {
+                    const float4 pi = __ldg(reinterpret_cast<const float4*>(a.Pi + (int64_t)S.dst[r] * 64) + cg);
+                    const float4 pj = __ldg(reinterpret_cast<const float4*>(a.Pj + (int64_t)S.src[r] * 64) + cg);
+                    // same association as the reference's single dot product is not
+                    // reproducible anyway; order: (Pi + Pj) + C e
+                    hv.x = fmaxf((pi.x + pj.x) + acc[i][0], 0.f);
+                    hv.y = fmaxf((pi.y + pj.y) + acc[i][1], 0.f);
+                    hv.z = fmaxf((pi.z + pj.z) + acc[i][2], 0.f);
+                    hv.w = fmaxf((pi.w + pj.w) + acc[i][3], 0.f);
+                }
+                *reinterpret_cast<float4*>(&S.H[r][4 * cg]) = hv;
+            }
+            __syncthreads();
+
+            // ---- m = W2 hidden + b2 -----------------------------------------------------
+            {
+                const float4 bb = *reinterpret_cast<const float4*>(&S.b2[4 * cg]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { acc[i][0] = bb.x; acc[i][1] = bb.y; acc[i][2] = bb.z; acc[i][3] = bb.w; }
+            }
+            gemm64(S.H, S.Wb, rg, cg, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(&S.A[8 * rg + i][4 * cg]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            __syncthreads();
+
+            // ---- store e_l tile + segmented PNA reduction --------------------------------
+            if (a.m_out) {
+                float4* g = reinterpret_cast<float4*>(a.m_out + (int64_t)t0 * 64);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    int idx = it * 256 + tid;
+                    int r = idx >> 4, c4 = idx & 15;
+                    if (r < nrows) __stcs(g + idx, *reinterpret_cast<const float4*>(&S.A[r][4 * c4]));
+                }
+            }
+            tile_reduce_scan(&S.A[0][0], LDT, S.dst, nrows, t0, &S.red, a.out);
+            __syncthreads();
+            if (tid < 64) tile_reduce_chain(nrows, &S.red, carry, a.out);
+            // next iteration's loads touch S.A / S.dst only; phase B reads S.red only, and
+            // S.H (aliasing S.red) is next written after the following __syncthreads.
+        }
+        if (tid < 64) carry_flush(carry, a.out);
+    }
+}
+
+// ---- block-1 vertex projections from raw features --------------------------------------
+__global__ void k_node_proj_first(const float* __restrict__ x, int Dv, const float* __restrict__ W1,
+                                  int ldW1, const float* __restrict__ b1, int64_t N,
+                                  float* __restrict__ Pi, float* __restrict__ Pj) {
+    int64_t total = N * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t v = t >> 6;
+        int o = (int)(t & 63);
+        float pi = b1[o], pj = 0.f;
+        for (int d = 0; d < Dv; ++d) {
+            float xv = x[v * Dv + d];
+            pi = fmaf(W1[o * ldW1 + d], xv, pi);
+            pj = fmaf(W1[o * ldW1 + Dv + d], xv, pj);
+        }
+        Pi[t] = pi;
+        Pj[t] = pj;
+    }
+}
+
+// ---- per-vertex update MLP (+ next projections | head) ----------------------------------
+constexpr int TV = 32;  // vertices per tile
+
+struct NodeArgs {
+    const float* agg;      // [N,256]
+    const float* h_in;     // [N,Dv]
+    int Dv;
+    const int32_t* seg_off;
+    const float *U1, *c1, *U2, *c2;  // update MLP
+    // next block (LAST == false)
+    const float* W1n; int ldW1n; const float* b1n;
+    // head (LAST == true)
+    const float *F1, *f1, *F2, *f2, *F3, *f3; int Dg;
+    const float* gfeat; const int32_t* vgraph;
+    int64_t N;
+    float* h_out;          // [N,64]
+    float* Pi; float* Pj;  // [N,64] next block's projections
+    float* q;              // [N]
+};
+
+// out[v] = bias + sum_k in[v][k] * Wt[k][o] for the thread's 8 vertices
+__device__ __forceinline__ void dense8(const float* in_s, int ld, int K, const float* Wt, float bias,
+                                       int o, int vb, float acc[8]) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] = bias;
+    int k = 0;
+    for (; k + 4 <= K; k += 4) {
+        const float w0 = Wt[(k + 0) * 64 + o], w1 = Wt[(k + 1) * 64 + o];
+        const float w2 = Wt[(k + 2) * 64 + o], w3 = Wt[(k + 3) * 64 + o];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const float4 xv = *reinterpret_cast<const float4*>(&in_s[(vb + v) * ld + k]);
+            acc[v] = fmaf(xv.x, w0, acc[v]);
+            acc[v] = fmaf(xv.y, w1, acc[v]);
+            acc[v] = fmaf(xv.z, w2, acc[v]);
+            acc[v] = fmaf(xv.w, w3, acc[v]);
+        }
+    }
+    for (; k < K; ++k) {
+        const float w0 = Wt[k * 64 + o];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[v] = fmaf(in_s[(vb + v) * ld + k], w0, acc[v]);
+    }
+}
+
+__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+
+template <bool LAST>
+__global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
+    extern __shared__ __align__(16) float smem_f[];
+    const int K1 = 256 + a.Dv;
+    const int ld_in = round4(K1) + 4;
+    const int KX = LAST ? (64 + a.Dg) : 64;     // rows of the first "extra" matrix
+    const int ld_m2 = round4(KX) + 4;
+    float* U1t = smem_f;                        // [K1][64]
+    float* U2t = U1t + (size_t)K1 * 64;         // [64][64]
+    float* X1t = U2t + 64 * 64;                 // LAST: F1t [64+Dg][64]; else At [64][64]
+    float* X2t = X1t + (size_t)KX * 64;         // LAST: F2t [64][64];    else Bt [64][64]
+    float* in_s = X2t + 64 * 64;                // [TV][ld_in]
+    float* mid_s = in_s + (size_t)TV * ld_in;   // [TV][68]
+    float* mid2_s = mid_s + TV * 68;            // [TV][ld_m2]
+    const int tid = threadIdx.x;
+    const int o = tid & 63, vg = tid >> 6, vb = vg * 8;
+
+    for (int t = tid; t < K1 * 64; t += 256) { int oo = t & 63, k = t >> 6; U1t[k * 64 + oo] = a.U1[oo * K1 + k]; }
+    for (int t = tid; t < 64 * 64; t += 256) { int oo = t & 63, k = t >> 6; U2t[k * 64 + oo] = a.U2[oo * 64 + k]; }
+    if (LAST) {
+        for (int t = tid; t < KX * 64; t += 256) { int oo = t & 63, k = t >> 6; X1t[k * 64 + oo] = a.F1[oo * KX + k]; }
+        for (int t = tid; t < 64 * 64; t += 256) { int oo = t & 63, k = t >> 6; X2t[k * 64 + oo] = a.F2[oo * 64 + k]; }
+    } else {
+        for (int t = tid; t < 64 * 64; t += 256) {
+            int oo = t & 63, k = t >> 6;
+            X1t[k * 64 + oo] = a.W1n[oo * a.ldW1n + k];        // A: columns [0,64)
+            X2t[k * 64 + oo] = a.W1n[oo * a.ldW1n + 64 + k];   // B: columns [64,128)
+        }
+    }
+    const float c1 = a.c1[o], c2 = a.c2[o];
+    const float bx1 = LAST ? a.f1[o] : a.b1n[o];
+    const float bx2 = LAST ? a.f2[o] : 0.f;
+    __syncthreads();
+
+    const int64_t n_tiles = (a.N + TV - 1) / TV;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t vt = tile * TV;
+        // [agg | h_in] -> smem; empty segments take the scatter defaults (0,0,0,sqrt(eps))
+        for (int t = tid; t < TV * 64; t += 256) {
+            int v = t >> 6, c4 = t & 63;   // 64 float4 per vertex row of agg
+            int64_t gv = vt + v;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gv < a.N) {
+                if (a.seg_off[gv + 1] > a.seg_off[gv]) val = __ldg(reinterpret_cast<const float4*>(a.agg + gv * 256) + c4);
+                else if (c4 >= 48) { const float s = sqrtf(PNA_EPS); val = make_float4(s, s, s, s); }
+            }
+            *reinterpret_cast<float4*>(&in_s[v * ld_in + 4 * c4]) = val;
+        }
+        for (int t = tid; t < TV * a.Dv; t += 256) {
+            int v = t / a.Dv, d = t - v * a.Dv;
+            int64_t gv = vt + v;
+            in_s[v * ld_in + 256 + d] = (gv < a.N) ? a.h_in[gv * a.Dv + d] : 0.f;
+        }
+        __syncthreads();
+        float acc[8];
+        dense8(in_s, ld_in, K1, U1t, c1, o, vb, acc);                  // update_mlp.0 + ReLU
+#pragma unroll
+        for (int v = 0; v < 8; ++v) mid_s[(vb + v) * 68 + o] = fmaxf(acc[v], 0.f);
+        __syncthreads();
+        dense8(mid_s, 68, 64, U2t, c2, o, vb, acc);                    // update_mlp.2
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            int64_t gv = vt + vb + v;
+            mid2_s[(vb + v) * ld_m2 + o] = acc[v];
+            if (gv < a.N) a.h_out[gv * 64 + o] = acc[v];
+        }
+        if (LAST && a.Dg > 0) {
+            for (int t = tid; t < TV * a.Dg; t += 256) {
+                int v = t / a.Dg, d = t - v * a.Dg;
+                int64_t gv = vt + v;
+                mid2_s[v * ld_m2 + 64 + d] = (gv < a.N) ? a.gfeat[(int64_t)a.vgraph[gv] * a.Dg + d] : 0.f;
+            }
+        }
+        __syncthreads();
+        if (!LAST) {
+            dense8(mid2_s, ld_m2, 64, X1t, bx1, o, vb, acc);           // Pi = A h + b1
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { int64_t gv = vt + vb + v; if (gv < a.N) a.Pi[gv * 64 + o] = acc[v]; }
+            dense8(mid2_s, ld_m2, 64, X2t, 0.f, o, vb, acc);           // Pj = B h
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { int64_t gv = vt + vb + v; if (gv < a.N) a.Pj[gv * 64 + o] = acc[v]; }
+        } else {
+            dense8(mid2_s, ld_m2, KX, X1t, bx1, o, vb, acc);           // fc1 + ReLU
+#pragma unroll
+            for (int v = 0; v < 8; ++v) mid_s[(vb + v) * 68 + o] = fmaxf(acc[v], 0.f);
+            __syncthreads();
+            dense8(mid_s, 68, 64, X2t, bx2, o, vb, acc);               // fc2 + ReLU
+            __syncthreads();   // everyone done reading mid_s? (mid2_s is the target) keep order simple
+#pragma unroll
+            for (int v = 0; v < 8; ++v) mid2_s[(vb + v) * ld_m2 + o] = fmaxf(acc[v], 0.f);
+            __syncthreads();
+            if (tid < TV) {                                            // fc3: one output
+                int64_t gv = vt + tid;
+                if (gv < a.N) {
+                    float s = a.f3[0];
+                    for (int k = 0; k < 64; ++k) s = fmaf(mid2_s[tid * ld_m2 + k], __ldg(a.F3 + k), s);
+                    a.q[gv] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t node_smem_bytes(int Dv, int Dg, bool last) {
+    int K1 = 256 + Dv;
+    int KX = last ? 64 + Dg : 64;
+    size_t f = (size_t)K1 * 64 + 64 * 64 + (size_t)KX * 64 + 64 * 64 + (size_t)TV * (round4(K1) + 4) +
+               (size_t)TV * 68 + (size_t)TV * (round4(KX) + 4);
+    return f * sizeof(float);
+}
+
+// ---- host-side orchestration -------------------------------------------------------------
+struct Stash {
+    float* e[4];
+    float* h[5];
+    float* agg[5];
+    float* var[5];
+    int32_t* amin[5];
+    int32_t* amax[5];
+};
+
+size_t stash_bytes(int64_t N, int64_t E) {
+    size_t b = 0;
+    b += 4 * align_up((size_t)E * 64 * 4);
+    b += 5 * align_up((size_t)N * 64 * 4);
+    b += 5 * align_up((size_t)N * 256 * 4);
+    b += 5 * align_up((size_t)N * 64 * 4);
+    b += 10 * align_up((size_t)N * 64 * 4);
+    return b + 256;
+}
+
+Stash carve_stash(void* p, int64_t N, int64_t E) {
+    Arena ar(p, (size_t)-1);
+    Stash s;
+    for (int i = 0; i < 4; ++i) s.e[i] = ar.take<float>((size_t)E * 64);
+    for (int i = 0; i < 5; ++i) s.h[i] = ar.take<float>((size_t)N * 64);
+    for (int i = 0; i < 5; ++i) s.agg[i] = ar.take<float>((size_t)N * 256);
+    for (int i = 0; i < 5; ++i) s.var[i] = ar.take<float>((size_t)N * 64);
+    for (int i = 0; i < 5; ++i) s.amin[i] = ar.take<int32_t>((size_t)N * 64);
+    for (int i = 0; i < 5; ++i) s.amax[i] = ar.take<int32_t>((size_t)N * 64);
+    return s;
+}
+
+static int set_smem_attrs() {
+    static bool done = false;
+    if (done) return GCRL_OK;
+    GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem)));
+    GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EdgeSmem)));
+    GCRL_CUDA(cudaFuncSetAttribute(k_node_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    GCRL_CUDA(cudaFuncSetAttribute(k_node_update<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    done = true;
+    return GCRL_OK;
+}
+
+int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* Pj, const float* e_prev,
+                    const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
+                    float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st) {
+    if (E == 0) return GCRL_OK;
+    EdgeArgs a;
+    a.Pi = Pi; a.Pj = Pj; a.e_prev = e_prev; a.De = b.De;
+    a.W1 = b.W1; a.ldW1 = 2 * b.Dv + b.De; a.coff = 2 * b.Dv;
+    a.W2 = b.W2; a.b2 = b.b2;
+    a.seg_off = seg_off; a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
+    a.m_out = m_out;
+    a.out.agg = agg; a.out.var = var; a.out.amin = amin; a.out.amax = amax; a.out.seg_off = seg_off;
+    int64_t items = (E + ITEM_EDGES - 1) / ITEM_EDGES;
+    int64_t grid = (int64_t)sm_count() * 2;
+    if (grid > items) grid = items;
+    if (first) k_edge_fwd<true><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
+    else k_edge_fwd<false><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+int launch_node_update(const NetW& net, int l /*0-based*/, const float* agg, const float* h_in,
+                       const int32_t* seg_off, const float* gfeat, const int32_t* vgraph, int64_t N,
+                       float* h_out, float* Pi, float* Pj, float* q, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    const BlockW& b = net.blk[l];
+    const bool last = (l == GCRL_N_BLOCKS - 1);
+    NodeArgs a;
+    a.agg = agg; a.h_in = h_in; a.Dv = b.Dv; a.seg_off = seg_off;
+    a.U1 = b.U1; a.c1 = b.c1; a.U2 = b.U2; a.c2 = b.c2;
+    a.W1n = nullptr; a.ldW1n = 0; a.b1n = nullptr;
+    a.F1 = a.f1 = a.F2 = a.f2 = a.F3 = a.f3 = nullptr; a.Dg = 0;
+    a.gfeat = gfeat; a.vgraph = vgraph;
+    a.N = N; a.h_out = h_out; a.Pi = Pi; a.Pj = Pj; a.q = q;
+    if (last) {
+        a.F1 = net.head.F1; a.f1 = net.head.f1; a.F2 = net.head.F2; a.f2 = net.head.f2;
+        a.F3 = net.head.F3; a.f3 = net.head.f3; a.Dg = net.head.Dg;
+    } else {
+        const BlockW& nb = net.blk[l + 1];
+        a.W1n = nb.W1; a.ldW1n = 2 * nb.Dv + nb.De; a.b1n = nb.b1;
+    }
+    size_t smem = node_smem_bytes(b.Dv, net.head.Dg, last);
+    int64_t tiles = (N + TV - 1) / TV;
+    int64_t grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    if (last) k_node_update<true><<<(int)grid, 256, smem, st>>>(a);
+    else k_node_update<false><<<(int)grid, 256, smem, st>>>(a);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+}  // namespace gcrl
+
+using namespace gcrl;
+
+extern "C" {
+
+size_t gcrl_gn_stash_bytes(int64_t N, int64_t E) { return stash_bytes(N, E); }
+
+size_t gcrl_gn_forward_workspace_bytes(int64_t N, int64_t E, int with_stash) {
+    size_t b = 2 * align_up((size_t)N * 64 * 4);  // Pi, Pj
+    if (!with_stash) {
+        b += 2 * align_up((size_t)E * 64 * 4);    // e ping-pong
+        b += 2 * align_up((size_t)N * 64 * 4);    // h ping-pong
+        b += align_up((size_t)N * 256 * 4);       // agg
+    }
+    return b + 256;
+}
+
+static int check_dims(int vdim, int edim, int gdim) {
+    GCRL_CHECK_ARG(vdim >= 1 && vdim <= 64 && edim >= 1 && edim <= 64 && gdim >= 0 && gdim <= 64);
+    return GCRL_OK;
+}
+
+int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N, int64_t E,
+                    const int32_t* seg_off, const int32_t* src, const int32_t* dst, const float* x,
+                    const float* eattr, const float* gfeat, const int32_t* vgraph, void* stash_p,
+                    float* h_out, float* q_out, void* ws, size_t ws_bytes, int math_mode, void* stream) {
+    int rc = check_dims(vdim, edim, gdim);
+    if (rc) return rc;
+    GCRL_CHECK_ARG(N >= 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31));
+    if (N == 0) return GCRL_OK;
+    GCRL_CHECK_ARG(params && seg_off && x && q_out && (E == 0 || (src && dst && eattr)));
+    GCRL_CHECK_ARG(gdim == 0 || (gfeat && vgraph));
+    if (math_mode != GCRL_MATH_FP32) {
+        set_error("gcrl_gn_forward: math_mode %d not available in this build", math_mode);
+        return GCRL_ERR_INVALID;
+    }
+    if (!ws || ws_bytes < gcrl_gn_forward_workspace_bytes(N, E, stash_p != nullptr)) {
+        set_error("gcrl_gn_forward: workspace too small");
+        return GCRL_ERR_WORKSPACE;
+    }
+    rc = set_smem_attrs();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    NetW net = make_net(params, vdim, edim, gdim);
+    Arena ar(ws, ws_bytes);
+    float* Pi = ar.take<float>((size_t)N * 64);
+    float* Pj = ar.take<float>((size_t)N * 64);
+    Stash S;
+    float *eb[2] = {nullptr, nullptr}, *hb[2] = {nullptr, nullptr}, *aggb = nullptr;
+    if (stash_p) {
+        S = carve_stash(stash_p, N, E);
+    } else {
+        eb[0] = ar.take<float>((size_t)E * 64);
+        eb[1] = ar.take<float>((size_t)E * 64);
+        hb[0] = ar.take<float>((size_t)N * 64);
+        hb[1] = ar.take<float>((size_t)N * 64);
+        aggb = ar.take<float>((size_t)N * 256);
+    }
+    {
+        const BlockW& b = net.blk[0];
+        int64_t total = N * 64;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
+        GCRL_LAUNCH_CHECK();
+    }
+    const float* e_prev = eattr;
+    const float* h_prev = x;
+    for (int l = 0; l < GCRL_N_BLOCKS; ++l) {
+        const bool last = (l == GCRL_N_BLOCKS - 1);
+        float* e_out = last ? nullptr : (stash_p ? S.e[l] : eb[l & 1]);
+        float* agg = stash_p ? S.agg[l] : aggb;
+        float* hl = stash_p ? S.h[l] : hb[l & 1];
+        rc = launch_edge_fwd(net.blk[l], l == 0, Pi, Pj, e_prev, seg_off, src, dst, N, E, e_out, agg,
+                             stash_p ? S.var[l] : nullptr, stash_p ? S.amin[l] : nullptr,
+                             stash_p ? S.amax[l] : nullptr, st);
+        if (rc) return rc;
+        rc = launch_node_update(net, l, agg, h_prev, seg_off, gfeat, vgraph, N, hl, Pi, Pj, q_out, st);
+        if (rc) return rc;
+        e_prev = e_out;
+        h_prev = hl;
+    }
+    if (h_out) GCRL_CUDA(cudaMemcpyAsync(h_out, h_prev, (size_t)N * 64 * 4, cudaMemcpyDeviceToDevice, st));
+    return GCRL_OK;
+}
+
+int gcrl_gn_block_forward(const float* params, int vdim, int edim, int gdim, int block, int64_t N,
+                          int64_t E, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
+                          const float* x, const float* eattr, float* msg_out, float* upd_out,
+                          void* ws, size_t ws_bytes, int math_mode, void* stream) {
+    int rc = check_dims(vdim, edim, gdim);
+    if (rc) return rc;
+    GCRL_CHECK_ARG(block >= 1 && block <= GCRL_N_BLOCKS);
+    GCRL_CHECK_ARG(N >= 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31));
+    if (N == 0) return GCRL_OK;
+    GCRL_CHECK_ARG(params && seg_off && x && upd_out && (E == 0 || (src && dst && eattr && msg_out)));
+    if (math_mode != GCRL_MATH_FP32) {
+        set_error("gcrl_gn_block_forward: math_mode %d not available in this build", math_mode);
+        return GCRL_ERR_INVALID;
+    }
+    size_t need = 2 * align_up((size_t)N * 64 * 4) + align_up((size_t)N * 256 * 4) + align_up((size_t)N * 4) + 256;
+    if (!ws || ws_bytes < need) {
+        set_error("gcrl_gn_block_forward: workspace too small (need %zu)", need);
+        return GCRL_ERR_WORKSPACE;
+    }
+    rc = set_smem_attrs();
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    NetW net = make_net(params, vdim, edim, gdim);
+    const BlockW& b = net.blk[block - 1];
+    Arena ar(ws, ws_bytes);
+    float* Pi = ar.take<float>((size_t)N * 64);
+    float* Pj = ar.take<float>((size_t)N * 64);
+    float* agg = ar.take<float>((size_t)N * 256);
+    float* qtmp = ar.take<float>((size_t)N);
+    {
+        int64_t total = N * 64;
+        int64_t blocks = (total + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
+        GCRL_LAUNCH_CHECK();
+    }
+    rc = launch_edge_fwd(b, b.De != 64 || block == 1, Pi, Pj, eattr, seg_off, src, dst, N, E, msg_out, agg,
+                         nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    // the vertex kernel also emits the next block's projections / head; they land in Pi/Pj/qtmp
+    return launch_node_update(net, block - 1, agg, x, seg_off, nullptr, nullptr, N, upd_out, Pi, Pj, qtmp, st);
+}
+
+}  // extern "C"

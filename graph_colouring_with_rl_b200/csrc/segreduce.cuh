@@ -1,0 +1,169 @@
+// segreduce.cuh -- CTA-level segmented PNA reduction of a 128-row message tile held in
+// shared memory (rows = consecutive destination-major edge slots).  Shared by the fused
+// edge kernels; deterministic (fixed combination order, no atomics).
+//
+// 256 threads: col = tid & 63, quarter q = tid >> 6 scans rows [32q, 32q+32) of its column.
+// A quarter emits a "head" partial (rows before its first segment boundary, possibly the
+// continuation of an earlier quarter / tile), finalises segments that start and end inside
+// it, and emits a "tail" partial (rows after its last boundary).  Threads 0..63 then chain
+// carry (+) head / tail across the four quarters; the carry lives in their registers across
+// the tiles of a work item.
+#pragma once
+#include "common.cuh"
+
+namespace gcrl {
+
+struct Stat {
+    float sum, sq, mn, mx;
+    int32_t amn, amx;
+};
+__device__ __forceinline__ void stat_init(Stat& s) {
+    s.sum = 0.f; s.sq = 0.f; s.mn = INFINITY; s.mx = -INFINITY;
+    s.amn = 0x7fffffff; s.amx = 0x7fffffff;
+}
+// rows fed in ascending slot order; strict comparisons keep the FIRST extremum
+// (torch_scatter CPU kernel: `if (src < out) {out = src; arg = e}` in edge order).
+__device__ __forceinline__ void stat_add(Stat& s, float v, int32_t slot) {
+    s.sum += v;
+    s.sq = fmaf(v, v, s.sq);
+    if (v < s.mn) { s.mn = v; s.amn = slot; }
+    if (v > s.mx) { s.mx = v; s.amx = slot; }
+}
+__device__ __forceinline__ void stat_merge(Stat& a, const Stat& b) {
+    a.sum += b.sum;
+    a.sq += b.sq;
+    if (b.mn < a.mn || (b.mn == a.mn && b.amn < a.amn)) { a.mn = b.mn; a.amn = b.amn; }
+    if (b.mx > a.mx || (b.mx == a.mx && b.amx < a.amx)) { a.mx = b.mx; a.amx = b.amx; }
+}
+// principal_neighbourhood_aggregation.py:45-46,57-64.  Non-contracted mul/sub: the variance
+// is cancellation-prone and the reference rounds mean*mean and the subtraction separately.
+__device__ __forceinline__ void stat_final(const Stat& s, int32_t deg, float& mean, float& mn,
+                                           float& mx, float& sd, float& var) {
+    if (deg <= 0) {  // empty segment: scatter leaves zeros
+        mean = 0.f; mn = 0.f; mx = 0.f; var = 0.f; sd = sqrtf(PNA_EPS);
+        return;
+    }
+    float cnt = (float)deg;
+    mean = __fdiv_rn(s.sum, cnt);
+    float msq = __fdiv_rn(s.sq, cnt);
+    var = __fsub_rn(msq, __fmul_rn(mean, mean));
+    sd = sqrtf(__fadd_rn(fmaxf(var, 0.f), PNA_EPS));
+    mn = s.mn; mx = s.mx;
+}
+
+struct AggOut {
+    float* agg;       // [N,256] mean|min|max|std
+    float* var;       // [N,64] raw variance (relu' mask for backward) or null
+    int32_t* amin;    // [N,64] or null
+    int32_t* amax;    // [N,64] or null
+    const int32_t* seg_off;
+};
+
+__device__ __forceinline__ void agg_write(const AggOut& o, int32_t v, int col, const Stat& s) {
+    int32_t deg = o.seg_off[v + 1] - o.seg_off[v];
+    float mean, mn, mx, sd, var;
+    stat_final(s, deg, mean, mn, mx, sd, var);
+    float* a = o.agg + (int64_t)v * 256;
+    a[col] = mean; a[64 + col] = mn; a[128 + col] = mx; a[192 + col] = sd;
+    if (o.var) o.var[(int64_t)v * 64 + col] = var;
+    if (o.amin) o.amin[(int64_t)v * 64 + col] = s.amn;
+    if (o.amax) o.amax[(int64_t)v * 64 + col] = s.amx;
+}
+
+// scratch carved from shared memory: 2 (head/tail) x 6 fields x 4 quarters x 64 cols + ids
+struct RedScratch {
+    float f[2][4][4][64];     // [head/tail][sum,sq,mn,mx][quarter][col]
+    int32_t a[2][2][4][64];   // [head/tail][amn,amx][quarter][col]
+    int32_t head_dst[4];
+    int32_t tail_dst[4];      // -1: quarter saw no boundary (everything is in head)
+};
+
+struct Carry {
+    Stat s;
+    int32_t dst;  // -1 = empty
+};
+
+// Phase A: all 256 threads.  M_s: tile [128][ld] in smem, dst_s[128] destination ids of rows.
+__device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const int32_t* dst_s,
+                                                 int nrows, int32_t slot0, RedScratch* sc,
+                                                 const AggOut& out) {
+    const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int r0 = q * 32;
+    const int r1 = min(r0 + 32, nrows);
+    if (r0 >= r1) return;
+    Stat cur;
+    stat_init(cur);
+    int32_t cd = dst_s[r0];
+    const int32_t hd = cd;
+    bool seen = false;
+    for (int r = r0; r < r1; ++r) {
+        int32_t d = dst_s[r];
+        if (d != cd) {
+            if (!seen) {
+                sc->f[0][0][q][col] = cur.sum; sc->f[0][1][q][col] = cur.sq;
+                sc->f[0][2][q][col] = cur.mn;  sc->f[0][3][q][col] = cur.mx;
+                sc->a[0][0][q][col] = cur.amn; sc->a[0][1][q][col] = cur.amx;
+                seen = true;
+            } else {
+                agg_write(out, cd, col, cur);   // segment lies wholly inside this quarter
+            }
+            stat_init(cur);
+            cd = d;
+        }
+        stat_add(cur, M_s[r * ld + col], slot0 + r);
+    }
+    const int w = seen ? 1 : 0;
+    sc->f[w][0][q][col] = cur.sum; sc->f[w][1][q][col] = cur.sq;
+    sc->f[w][2][q][col] = cur.mn;  sc->f[w][3][q][col] = cur.mx;
+    sc->a[w][0][q][col] = cur.amn; sc->a[w][1][q][col] = cur.amx;
+    if (col == 0) {
+        sc->head_dst[q] = hd;
+        sc->tail_dst[q] = seen ? cd : -1;
+    }
+}
+
+// Phase B: threads 0..63 only (after a __syncthreads following phase A).
+__device__ __forceinline__ void tile_reduce_chain(int nrows, const RedScratch* sc, Carry& c,
+                                                  const AggOut& out) {
+    const int col = threadIdx.x;
+    for (int q = 0; q < 4; ++q) {
+        if (q * 32 >= nrows) break;
+        Stat h;
+        h.sum = sc->f[0][0][q][col]; h.sq = sc->f[0][1][q][col];
+        h.mn = sc->f[0][2][q][col];  h.mx = sc->f[0][3][q][col];
+        h.amn = sc->a[0][0][q][col]; h.amx = sc->a[0][1][q][col];
+        const int32_t hd = sc->head_dst[q];
+        if (c.dst == hd) {
+            stat_merge(c.s, h);
+        } else {
+            if (c.dst >= 0) agg_write(out, c.dst, col, c.s);
+            c.s = h; c.dst = hd;
+        }
+        const int32_t td = sc->tail_dst[q];
+        if (td >= 0) {
+            agg_write(out, c.dst, col, c.s);
+            c.s.sum = sc->f[1][0][q][col]; c.s.sq = sc->f[1][1][q][col];
+            c.s.mn = sc->f[1][2][q][col];  c.s.mx = sc->f[1][3][q][col];
+            c.s.amn = sc->a[1][0][q][col]; c.s.amx = sc->a[1][1][q][col];
+            c.dst = td;
+        }
+    }
+}
+
+__device__ __forceinline__ void carry_flush(Carry& c, const AggOut& out) {
+    if (c.dst >= 0) agg_write(out, c.dst, threadIdx.x, c.s);
+    c.dst = -1;
+}
+
+// lower_bound over seg_off[0..N]: first v in [0,N] with seg_off[v] >= key, clamped to N
+__device__ __forceinline__ int32_t seg_lower_bound(const int32_t* __restrict__ seg_off, int32_t N,
+                                                   int64_t key) {
+    int32_t lo = 0, hi = N;  // answer in [lo, hi]
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if ((int64_t)seg_off[mid] >= key) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+}  // namespace gcrl
