@@ -1,0 +1,128 @@
+"""ctypes binding of libgcrl_b200.so (include/gcrl_b200.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or
+a kernel entry point is called without a CUDA device, an exception is raised.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, 'libgcrl_b200.so')
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), 'include', 'gcrl_b200.h')
+
+GCRL_MATH_FP32 = 0
+GCRL_MATH_TF32 = 1
+GCRL_MATH_3XTF32 = 2
+
+_lib = None
+
+c_void_p, c_int, c_int32, c_int64, c_size_t, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float)
+P = c_void_p
+
+# name -> (restype, argtypes); must list every function include/gcrl_b200.h declares
+# (tests/test_abi.py parses the header and checks both directions).
+SIGNATURES = {
+    'gcrl_last_error': (ctypes.c_char_p, []),
+    'gcrl_version': (c_int, []),
+    'gcrl_sm_count': (c_int, []),
+    'gcrl_param_layout': (c_int, [c_int, c_int, c_int, P]),
+    'gcrl_pack_workspace_bytes': (c_size_t, [c_int64, c_int64]),
+    'gcrl_pack': (c_int, [P, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    'gcrl_pack_dense_workspace_bytes': (c_size_t, [c_int32]),
+    'gcrl_pack_dense': (c_int, [P, P, P, c_int32, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),
+    'gcrl_permute_rows': (c_int, [P, P, P, c_int64, c_int32, c_int, P]),
+    'gcrl_pna_forward': (c_int, [P, P, c_int64, c_int64, c_int32, P, P, P, P, P]),
+    'gcrl_pna_backward': (c_int, [P, P, P, P, P, P, P, P, c_int64, c_int64, c_int32, P, P]),
+    'gcrl_segment_reduce': (c_int, [P, P, c_int64, c_int64, c_int32, c_int, P, P]),
+    'gcrl_gn_stash_bytes': (c_size_t, [c_int64, c_int64]),
+    'gcrl_gn_forward_workspace_bytes': (c_size_t, [c_int64, c_int64, c_int]),
+    'gcrl_gn_forward': (c_int, [P, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P, P, P, P, P, P, P,
+                                P, c_size_t, c_int, P]),
+    'gcrl_gn_block_forward': (c_int, [P, c_int, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P, P,
+                                      P, P, P, c_size_t, c_int, P]),
+    'gcrl_gn_backward_workspace_bytes': (c_size_t, [c_int64, c_int64]),
+    'gcrl_gn_backward': (c_int, [P, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P, P, P, P, P, P, P,
+                                 P, c_int, P, c_size_t, c_int, P]),
+    'gcrl_score_argmax': (c_int, [P, P, P, c_int32, P, P, P]),
+    'gcrl_td_target_loss': (c_int, [P, P, P, P, c_int32, P, P, P, c_float, c_int32, P, P, P, P, P]),
+    'gcrl_adam_soft_update': (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float,
+                                      c_int64, c_float, P]),
+    'gcrl_soft_update': (c_int, [P, P, c_int64, c_float, P]),
+    'gcrl_env_reset': (c_int, [P, P, P, P, c_int32, c_int64, P]),
+    'gcrl_env_step': (c_int, [P, P, P, c_int32, P, P, P, P, P, P, P]),
+    'gcrl_env_first_vertex': (c_int, [P, P, P, c_int32, P, P, P]),
+}
+
+
+def header_functions():
+    """Names of the functions declared in include/gcrl_b200.h."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gcrl_[a-z0-9_]+)\s*\(', text)))
+
+
+class GcrlError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """dlopen the library (building it first if absent) and attach the signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        if not build_if_missing:
+            raise GcrlError('libgcrl_b200.so not built (%s); run python -m graph_colouring_with_rl_b200.build' % LIB_PATH)
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().gcrl_last_error().decode(errors='replace')
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GcrlError('%s failed (%d): %s' % (what, rc, last_error()))
+
+
+def require_cuda(t, name='tensor'):
+    if not t.is_cuda:
+        raise GcrlError('%s must be a CUDA tensor: graph_colouring_with_rl_b200 has no CPU path' % name)
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), 'non-contiguous tensor passed to the C ABI'
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag='ws'):
+    """Grow-only byte workspace per (device, tag); stream-ordered reuse on the current stream."""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf

@@ -15,13 +15,9 @@
 // Work decomposition of k_edge_fwd: work item w owns the destination vertices whose segment
 // starts in [w*ITEM_EDGES, (w+1)*ITEM_EDGES) -- whole segments, found by binary search on
 // seg_off, so no cross-CTA combination and no atomics.  Persistent CTAs stride over items.
-#include "segreduce.cuh"
+#include "gn_common.cuh"
 
 namespace gcrl {
-
-constexpr int TILE = 128;         // edge rows per tile
-constexpr int LDT = 68;           // padded smem row stride (floats), keeps 16 B alignment
-constexpr int ITEM_EDGES = 2048;  // target edges per work item
 
 struct EdgeSmem {
     float Wa[64][64];  // Wa[k][o] = W1[o][2Dv + k]  (edge part of message_mlp.0, transposed)
@@ -53,29 +49,6 @@ struct EdgeArgs {
     float* m_out;         // [E,64] or null
     AggOut out;
 };
-
-// acc[8][4] += A[8rg+i][:] . W[:][4cg+j], K = 64
-__device__ __forceinline__ void gemm64(const float (*A)[LDT], const float (*W)[64], int rg, int cg,
-                                       float acc[8][4]) {
-#pragma unroll 2
-    for (int k4 = 0; k4 < 16; ++k4) {
-        float4 a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(&A[8 * rg + i][4 * k4]);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const float4 w = *reinterpret_cast<const float4*>(&W[4 * k4 + kk][4 * cg]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                acc[i][0] = fmaf(av, w.x, acc[i][0]);
-                acc[i][1] = fmaf(av, w.y, acc[i][1]);
-                acc[i][2] = fmaf(av, w.z, acc[i][2]);
-                acc[i][3] = fmaf(av, w.w, acc[i][3]);
-            }
-        }
-    }
-}
 
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 2) k_edge_fwd(const EdgeArgs a) {
@@ -235,6 +208,11 @@ struct NodeArgs {
     float* h_out;          // [N,64]
     float* Pi; float* Pj;  // [N,64] next block's projections
     float* q;              // [N]
+    float* u1_out;         // [N,64] relu(update_mlp.0) stash or null
+    float* y1_out;         // [N,64] relu(fc1) stash or null
+    float* y2_out;         // [N,64] relu(fc2) stash or null
+    int extra;             // 0: update MLP only (gcrl_gn_block_forward)
+    float* agg_fix;        // stash mode: empty-segment rows of agg get the scatter defaults
 };
 
 // out[v] = bias + sum_k in[v][k] * Wt[k][o] for the thread's 8 vertices
@@ -286,7 +264,7 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
     if (LAST) {
         for (int t = tid; t < KX * 64; t += 256) { int oo = t & 63, k = t >> 6; X1t[k * 64 + oo] = a.F1[oo * KX + k]; }
         for (int t = tid; t < 64 * 64; t += 256) { int oo = t & 63, k = t >> 6; X2t[k * 64 + oo] = a.F2[oo * 64 + k]; }
-    } else {
+    } else if (a.extra) {
         for (int t = tid; t < 64 * 64; t += 256) {
             int oo = t & 63, k = t >> 6;
             X1t[k * 64 + oo] = a.W1n[oo * a.ldW1n + k];        // A: columns [0,64)
@@ -294,7 +272,7 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
         }
     }
     const float c1 = a.c1[o], c2 = a.c2[o];
-    const float bx1 = LAST ? a.f1[o] : a.b1n[o];
+    const float bx1 = LAST ? a.f1[o] : (a.extra ? a.b1n[o] : 0.f);
     const float bx2 = LAST ? a.f2[o] : 0.f;
     __syncthreads();
 
@@ -308,7 +286,10 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gv < a.N) {
                 if (a.seg_off[gv + 1] > a.seg_off[gv]) val = __ldg(reinterpret_cast<const float4*>(a.agg + gv * 256) + c4);
-                else if (c4 >= 48) { const float s = sqrtf(PNA_EPS); val = make_float4(s, s, s, s); }
+                else {
+                    if (c4 >= 48) { const float s = sqrtf(PNA_EPS); val = make_float4(s, s, s, s); }
+                    if (a.agg_fix) reinterpret_cast<float4*>(a.agg_fix + gv * 256)[c4] = val;
+                }
             }
             *reinterpret_cast<float4*>(&in_s[v * ld_in + 4 * c4]) = val;
         }
@@ -321,7 +302,11 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
         float acc[8];
         dense8(in_s, ld_in, K1, U1t, c1, o, vb, acc);                  // update_mlp.0 + ReLU
 #pragma unroll
-        for (int v = 0; v < 8; ++v) mid_s[(vb + v) * 68 + o] = fmaxf(acc[v], 0.f);
+        for (int v = 0; v < 8; ++v) {
+            const float u = fmaxf(acc[v], 0.f);
+            mid_s[(vb + v) * 68 + o] = u;
+            if (a.u1_out && vt + vb + v < a.N) a.u1_out[(vt + vb + v) * 64 + o] = u;
+        }
         __syncthreads();
         dense8(mid_s, 68, 64, U2t, c2, o, vb, acc);                    // update_mlp.2
 #pragma unroll
@@ -338,7 +323,9 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
             }
         }
         __syncthreads();
-        if (!LAST) {
+        if (!LAST && !a.extra) {
+            // update MLP only
+        } else if (!LAST) {
             dense8(mid2_s, ld_m2, 64, X1t, bx1, o, vb, acc);           // Pi = A h + b1
 #pragma unroll
             for (int v = 0; v < 8; ++v) { int64_t gv = vt + vb + v; if (gv < a.N) a.Pi[gv * 64 + o] = acc[v]; }
@@ -348,12 +335,20 @@ __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
         } else {
             dense8(mid2_s, ld_m2, KX, X1t, bx1, o, vb, acc);           // fc1 + ReLU
 #pragma unroll
-            for (int v = 0; v < 8; ++v) mid_s[(vb + v) * 68 + o] = fmaxf(acc[v], 0.f);
+            for (int v = 0; v < 8; ++v) {
+                const float y = fmaxf(acc[v], 0.f);
+                mid_s[(vb + v) * 68 + o] = y;
+                if (a.y1_out && vt + vb + v < a.N) a.y1_out[(vt + vb + v) * 64 + o] = y;
+            }
             __syncthreads();
             dense8(mid_s, 68, 64, X2t, bx2, o, vb, acc);               // fc2 + ReLU
-            __syncthreads();   // everyone done reading mid_s? (mid2_s is the target) keep order simple
+            __syncthreads();   // mid2_s (fc1 input) fully consumed before it is overwritten
 #pragma unroll
-            for (int v = 0; v < 8; ++v) mid2_s[(vb + v) * ld_m2 + o] = fmaxf(acc[v], 0.f);
+            for (int v = 0; v < 8; ++v) {
+                const float y = fmaxf(acc[v], 0.f);
+                mid2_s[(vb + v) * ld_m2 + o] = y;
+                if (a.y2_out && vt + vb + v < a.N) a.y2_out[(vt + vb + v) * 64 + o] = y;
+            }
             __syncthreads();
             if (tid < TV) {                                            // fc3: one output
                 int64_t gv = vt + tid;
@@ -377,37 +372,6 @@ static size_t node_smem_bytes(int Dv, int Dg, bool last) {
 }
 
 // ---- host-side orchestration -------------------------------------------------------------
-struct Stash {
-    float* e[4];
-    float* h[5];
-    float* agg[5];
-    float* var[5];
-    int32_t* amin[5];
-    int32_t* amax[5];
-};
-
-size_t stash_bytes(int64_t N, int64_t E) {
-    size_t b = 0;
-    b += 4 * align_up((size_t)E * 64 * 4);
-    b += 5 * align_up((size_t)N * 64 * 4);
-    b += 5 * align_up((size_t)N * 256 * 4);
-    b += 5 * align_up((size_t)N * 64 * 4);
-    b += 10 * align_up((size_t)N * 64 * 4);
-    return b + 256;
-}
-
-Stash carve_stash(void* p, int64_t N, int64_t E) {
-    Arena ar(p, (size_t)-1);
-    Stash s;
-    for (int i = 0; i < 4; ++i) s.e[i] = ar.take<float>((size_t)E * 64);
-    for (int i = 0; i < 5; ++i) s.h[i] = ar.take<float>((size_t)N * 64);
-    for (int i = 0; i < 5; ++i) s.agg[i] = ar.take<float>((size_t)N * 256);
-    for (int i = 0; i < 5; ++i) s.var[i] = ar.take<float>((size_t)N * 64);
-    for (int i = 0; i < 5; ++i) s.amin[i] = ar.take<int32_t>((size_t)N * 64);
-    for (int i = 0; i < 5; ++i) s.amax[i] = ar.take<int32_t>((size_t)N * 64);
-    return s;
-}
-
 static int set_smem_attrs() {
     static bool done = false;
     if (done) return GCRL_OK;
@@ -439,23 +403,27 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
     return GCRL_OK;
 }
 
-int launch_node_update(const NetW& net, int l /*0-based*/, const float* agg, const float* h_in,
+int launch_node_update(const NetW& net, int l /*0-based*/, bool with_extra, const float* agg, const float* h_in,
                        const int32_t* seg_off, const float* gfeat, const int32_t* vgraph, int64_t N,
-                       float* h_out, float* Pi, float* Pj, float* q, cudaStream_t st) {
+                       float* h_out, float* Pi, float* Pj, float* q, float* u1_out, float* y1_out,
+                       float* y2_out, cudaStream_t st) {
     if (N == 0) return GCRL_OK;
     const BlockW& b = net.blk[l];
-    const bool last = (l == GCRL_N_BLOCKS - 1);
+    const bool last = with_extra && (l == GCRL_N_BLOCKS - 1);
     NodeArgs a;
+    a.extra = with_extra ? 1 : 0;
     a.agg = agg; a.h_in = h_in; a.Dv = b.Dv; a.seg_off = seg_off;
     a.U1 = b.U1; a.c1 = b.c1; a.U2 = b.U2; a.c2 = b.c2;
     a.W1n = nullptr; a.ldW1n = 0; a.b1n = nullptr;
     a.F1 = a.f1 = a.F2 = a.f2 = a.F3 = a.f3 = nullptr; a.Dg = 0;
     a.gfeat = gfeat; a.vgraph = vgraph;
     a.N = N; a.h_out = h_out; a.Pi = Pi; a.Pj = Pj; a.q = q;
+    a.u1_out = u1_out; a.y1_out = y1_out; a.y2_out = y2_out;
+    a.agg_fix = u1_out ? const_cast<float*>(agg) : nullptr;
     if (last) {
         a.F1 = net.head.F1; a.f1 = net.head.f1; a.F2 = net.head.F2; a.f2 = net.head.f2;
         a.F3 = net.head.F3; a.f3 = net.head.f3; a.Dg = net.head.Dg;
-    } else {
+    } else if (with_extra) {
         const BlockW& nb = net.blk[l + 1];
         a.W1n = nb.W1; a.ldW1n = 2 * nb.Dv + nb.De; a.b1n = nb.b1;
     }
@@ -533,7 +501,8 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         int64_t total = N * 64;
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
+        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N,
+                                                       stash_p ? S.Pi[0] : Pi, stash_p ? S.Pj[0] : Pj);
         GCRL_LAUNCH_CHECK();
     }
     const float* e_prev = eattr;
@@ -543,11 +512,15 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         float* e_out = last ? nullptr : (stash_p ? S.e[l] : eb[l & 1]);
         float* agg = stash_p ? S.agg[l] : aggb;
         float* hl = stash_p ? S.h[l] : hb[l & 1];
-        rc = launch_edge_fwd(net.blk[l], l == 0, Pi, Pj, e_prev, seg_off, src, dst, N, E, e_out, agg,
-                             stash_p ? S.var[l] : nullptr, stash_p ? S.amin[l] : nullptr,
-                             stash_p ? S.amax[l] : nullptr, st);
+        rc = launch_edge_fwd(net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
+                             seg_off, src, dst, N, E, e_out, agg, stash_p ? S.var[l] : nullptr,
+                             stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st);
         if (rc) return rc;
-        rc = launch_node_update(net, l, agg, h_prev, seg_off, gfeat, vgraph, N, hl, Pi, Pj, q_out, st);
+        float* Pin = (stash_p && !last) ? S.Pi[l + 1] : Pi;
+        float* Pjn = (stash_p && !last) ? S.Pj[l + 1] : Pj;
+        rc = launch_node_update(net, l, true, agg, h_prev, seg_off, gfeat, vgraph, N, hl, Pin, Pjn, q_out,
+                                stash_p ? S.u1[l] : nullptr, (stash_p && last) ? S.y1 : nullptr,
+                                (stash_p && last) ? S.y2 : nullptr, st);
         if (rc) return rc;
         e_prev = e_out;
         h_prev = hl;
@@ -595,8 +568,10 @@ int gcrl_gn_block_forward(const float* params, int vdim, int edim, int gdim, int
     rc = launch_edge_fwd(b, b.De != 64 || block == 1, Pi, Pj, eattr, seg_off, src, dst, N, E, msg_out, agg,
                          nullptr, nullptr, nullptr, st);
     if (rc) return rc;
-    // the vertex kernel also emits the next block's projections / head; they land in Pi/Pj/qtmp
-    return launch_node_update(net, block - 1, agg, x, seg_off, nullptr, nullptr, N, upd_out, Pi, Pj, qtmp, st);
+    // update MLP only (no next-block projections, no head)
+    (void)qtmp;
+    return launch_node_update(net, block - 1, false, agg, x, seg_off, nullptr, nullptr, N, upd_out, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, st);
 }
 
 }  // extern "C"

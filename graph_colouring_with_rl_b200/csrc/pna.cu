@@ -212,18 +212,13 @@ __global__ void k_pna_bwd(const float* __restrict__ msg, const float* __restrict
     }
 }
 
-__global__ void k_pna_fill_empty(const int32_t* __restrict__ seg_off, int64_t N, int32_t F,
-                                 float* __restrict__ out) {
-    // nothing to do: k_pna_fwd_* already emits (0,0,0,sqrt(eps)) for empty segments.
-}
-
 }  // namespace gcrl
 
 using namespace gcrl;
 
 extern "C" {
 
-int gcrl_pna_forward_ex(const float* msg, const int32_t* seg_off, int64_t N, int64_t E,
+int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t N, int64_t E,
                         int32_t F, float* out, int32_t* arg_min, int32_t* arg_max,
                         float* var_out, void* stream) {
     GCRL_CHECK_ARG(N >= 0 && E >= 0 && F >= 1);
@@ -247,18 +242,13 @@ int gcrl_pna_forward_ex(const float* msg, const int32_t* seg_off, int64_t N, int
     return GCRL_OK;
 }
 
-int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t N, int64_t E, int32_t F,
-                     float* out, int32_t* arg_min, int32_t* arg_max, void* stream) {
-    return gcrl_pna_forward_ex(msg, seg_off, N, E, F, out, arg_min, arg_max, nullptr, stream);
-}
-
-int gcrl_pna_backward_ex(const float* msg, const float* out, const float* var, const float* d_out,
+int gcrl_pna_backward(const float* msg, const float* out, const float* var, const float* d_out,
                          const int32_t* seg_off, const int32_t* dst, const int32_t* arg_min,
                          const int32_t* arg_max, int64_t N, int64_t E, int32_t F, float* d_msg,
                          void* stream) {
     GCRL_CHECK_ARG(N >= 0 && E >= 0 && F >= 1);
     if (E == 0) return GCRL_OK;
-    GCRL_CHECK_ARG(msg && out && d_out && seg_off && dst && arg_min && arg_max && d_msg);
+    GCRL_CHECK_ARG(msg && out && var && d_out && seg_off && dst && arg_min && arg_max && d_msg);
     int64_t total = E * F;
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 32;
@@ -267,14 +257,6 @@ int gcrl_pna_backward_ex(const float* msg, const float* out, const float* var, c
                                                               arg_min, arg_max, E, F, d_msg);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
-}
-
-int gcrl_pna_backward(const float* msg, const float* out, const float* d_out,
-                      const int32_t* seg_off, const int32_t* dst, const int32_t* arg_min,
-                      const int32_t* arg_max, int64_t N, int64_t E, int32_t F, float* d_msg,
-                      void* stream) {
-    return gcrl_pna_backward_ex(msg, out, nullptr, d_out, seg_off, dst, arg_min, arg_max, N, E, F,
-                                d_msg, stream);
 }
 
 int gcrl_segment_reduce(const float* msg, const int32_t* seg_off, int64_t N, int64_t E, int32_t F,

@@ -29,6 +29,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 typedef enum {
     GCRL_OK = 0,
@@ -45,6 +48,7 @@ typedef enum {
 /* math mode of the per-edge / per-vertex MLPs */
 #define GCRL_MATH_FP32 0     /* CUDA-core FFMA, fp32 operands and accumulate (parity mode) */
 #define GCRL_MATH_TF32 1     /* tcgen05 kind::tf32 tensor cores, fp32 accumulate in TMEM */
+#define GCRL_MATH_3XTF32 2   /* tcgen05 kind::tf32 with big/small operand split (near-fp32) */
 
 const char* gcrl_last_error(void);
 int gcrl_version(void);
@@ -86,13 +90,15 @@ int gcrl_permute_rows(const float* in, float* out, const int32_t* perm, int64_t 
  * architecture.py:62-66) ------------------------------------------------------------------
  * msg: [E,F] fp32 in INTERNAL order.  out: [N, 4F] = [mean | min | max | std] with
  * std = sqrt(relu(mean(x^2) - mean(x)^2) + 1e-5); empty segment -> (0,0,0,sqrt(1e-5)).
- * arg_min / arg_max: [N,F] int32 internal slot of the first extremum (may be NULL). */
+ * arg_min / arg_max: [N,F] int32 internal slot of the first extremum (may be NULL).
+ * var_out: [N,F] raw mean(x^2) - mean(x)^2 before the relu (may be NULL); the backward needs
+ * its sign for relu'. */
 int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t n_vertices,
                      int64_t n_edges, int32_t width, float* out, int32_t* arg_min,
-                     int32_t* arg_max, void* stream);
+                     int32_t* arg_max, float* var_out, void* stream);
 /* d_msg[E,F] from d_out[N,4F] (gradient routing of torch_scatter: mean -> 1/deg to every edge,
- * min/max -> the arg edge only, std through mean and mean-of-squares). */
-int gcrl_pna_backward(const float* msg, const float* out, const float* d_out,
+ * min/max -> the arg edge only, std through mean and mean-of-squares where var > 0). */
+int gcrl_pna_backward(const float* msg, const float* out, const float* var, const float* d_out,
                       const int32_t* seg_off, const int32_t* dst, const int32_t* arg_min,
                       const int32_t* arg_max, int64_t n_vertices, int64_t n_edges,
                       int32_t width, float* d_msg, void* stream);
@@ -179,6 +185,9 @@ int gcrl_env_first_vertex(const uint8_t* adj, const int64_t* adj_off, const int3
                           int32_t n_graphs, int32_t* action, int32_t* dist_counts,
                           void* stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,440 @@
+"""GPU parity tests: every C-ABI kernel entry point against the CPU oracle (oracle/) and the
+golden vectors of the unmodified reference (tests/golden/).  Integer work bit-exact; fp32 work
+within the tolerance written at each assert."""
+import numpy as np
+import pytest
+import torch
+
+import gcrl_testutil as util
+from oracle import env_oracle, gn_oracle
+
+pytestmark = pytest.mark.gpu
+
+GRAPHS = util.load_validation_graphs()
+DEV = 'cuda:0'
+
+
+def ops():
+    from graph_colouring_with_rl_b200 import ops as _ops
+    return _ops
+
+
+def batch_of(gids, rng, frac=0.4):
+    """-> (obs list, collated x/ei/ea CPU tensors, node counts, colour vectors)."""
+    obs, cols = [], []
+    for gi in gids:
+        g = GRAPHS[gi]
+        col = util.random_colours(g['n'], g['adj'], frac, rng)
+        obs.append(gn_oracle.observation(g['adj'], col, g['edge_list']))
+        cols.append(col)
+    x, ei, ea = gn_oracle.collate(obs)
+    return obs, x, ei, ea, [GRAPHS[gi]['n'] for gi in gids], cols
+
+
+def dense_inputs(gids):
+    adj = np.concatenate([GRAPHS[gi]['adj'].reshape(-1) for gi in gids])
+    ns = np.asarray([GRAPHS[gi]['n'] for gi in gids], dtype=np.int64)
+    adj_off = np.concatenate([[0], np.cumsum(ns * ns)[:-1]]).astype(np.int64)
+    node_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    return (torch.from_numpy(adj).to(DEV), torch.from_numpy(adj_off).to(DEV), torch.from_numpy(node_off).to(DEV),
+            int(ns.sum()), int((ns * (ns - 1)).sum()))
+
+
+# ---- graph batching: bit-exact ---------------------------------------------------------------
+def check_pack(ei, N, P):
+    E = ei.shape[1]
+    src, dst = ei[0].numpy(), ei[1].numpy()
+    order = np.lexsort((np.arange(E), dst))                 # destination-major, caller order inside
+    deg = np.bincount(dst, minlength=N)
+    seg = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
+    assert np.array_equal(P.seg_off.cpu().numpy(), seg)
+    assert np.array_equal(P.perm.cpu().numpy(), order.astype(np.int32))
+    assert np.array_equal(P.src.cpu().numpy(), src[order].astype(np.int32))
+    assert np.array_equal(P.dst.cpu().numpy(), dst[order].astype(np.int32))
+
+
+def test_pack_matches_collate_and_degrees():
+    rng = np.random.default_rng(0)
+    for gids in ([0], [3, 17, 58], list(range(20, 52)), [92, 93, 94, 95, 96, 97, 98, 99]):
+        _, x, ei, ea, ns, _ = batch_of(gids, rng)
+        P = ops().pack(ei.to(DEV), x.shape[0], validate=True)
+        check_pack(ei, x.shape[0], P)
+
+
+def test_pack_arbitrary_edge_order_and_sparse_graphs():
+    rng = np.random.default_rng(1)
+    for N, E in ((1, 0), (5, 0), (7, 13), (64, 500), (300, 5000)):
+        ei = torch.from_numpy(rng.integers(0, N, size=(2, E)).astype(np.int64))
+        P = ops().pack(ei.to(DEV), N, validate=True)
+        check_pack(ei, N, P)
+
+
+def test_pack_rejects_out_of_range_ids():
+    ei = torch.tensor([[0, 1, 5], [1, 0, 2]], dtype=torch.int64)
+    with pytest.raises(IndexError):
+        ops().pack(ei.to(DEV), 3, validate=True)
+
+
+def test_pack_dense_equals_pack_of_canonical_edge_list():
+    gids = [1, 2, 30, 77]
+    adj, adj_off, node_off, N, E = dense_inputs(gids)
+    Pd, eattr = ops().pack_dense(adj, adj_off, node_off, N, E)
+    obs = [gn_oracle.observation(GRAPHS[gi]['adj'], -np.ones(GRAPHS[gi]['n']), None) for gi in gids]
+    x, ei, ea = gn_oracle.collate(obs)
+    P = ops().pack(ei.to(DEV), N)
+    for a, b in zip(Pd[:4], P[:4]):
+        assert torch.equal(a, b)
+    assert torch.equal(eattr.cpu().view(-1), ea.view(-1)[P.perm.cpu().long()])
+
+
+def test_permute_rows_roundtrip():
+    rng = np.random.default_rng(2)
+    _, x, ei, ea, _, _ = batch_of([5, 6], rng)
+    P = ops().pack(ei.to(DEV), x.shape[0])
+    t = torch.randn(ei.shape[1], 7, device=DEV)
+    ti = ops().permute_rows(t, P.perm, True)
+    assert torch.equal(ti, t[P.perm.long()])
+    assert torch.equal(ops().permute_rows(ti, P.perm, False), t)
+
+
+# ---- PNA aggregation ---------------------------------------------------------------------------
+@pytest.mark.parametrize('F', [64, 5])
+def test_pna_forward_backward_vs_oracle(F):
+    rng = np.random.default_rng(3)
+    _, x, ei, ea, _, _ = batch_of([4, 40, 80], rng)
+    N, E = x.shape[0], ei.shape[1]
+    P = ops().pack(ei.to(DEV), N)
+    torch.manual_seed(0)
+    msg = torch.randn(E, F)
+    msg = torch.round(msg * 4) / 4                       # plenty of exact ties for the arg rule
+    msg_i = msg[P.perm.cpu().long()].to(DEV)            # internal order
+    out, amin, amax, var = ops().pna_forward(msg_i, P.seg_off, N, want_backward_state=True)
+    m = msg.clone().requires_grad_(True)
+    ref = gn_oracle.pna_aggregate(m, ei[1], N)
+    # mean/min/max exact up to summation order; std is cancellation-prone (tolerance 2e-6 abs)
+    np.testing.assert_allclose(out.cpu().numpy()[:, :F], ref.detach().numpy()[:, :F], rtol=1e-6, atol=1e-6)
+    assert torch.equal(out.cpu()[:, F:3 * F], ref.detach()[:, F:3 * F])
+    np.testing.assert_allclose(out.cpu().numpy()[:, 3 * F:], ref.detach().numpy()[:, 3 * F:], rtol=1e-5, atol=2e-6)
+    # arg indices: first edge (caller order) attaining the extremum
+    perm = P.perm.cpu().long()
+    ref_amin = gn_oracle.scatter_arg(msg, ei[1], N, False)
+    ref_amax = gn_oracle.scatter_arg(msg, ei[1], N, True)
+    assert torch.equal(perm[amin.cpu().long()], ref_amin)
+    assert torch.equal(perm[amax.cpu().long()], ref_amax)
+    # backward
+    d_out = torch.randn(N, 4 * F)
+    ref.backward(d_out)
+    d_msg = ops().pna_backward(msg_i, out, var, d_out.to(DEV), P.seg_off, P.dst, amin, amax)
+    d_ref = m.grad[perm]
+    np.testing.assert_allclose(d_msg.cpu().numpy(), d_ref.numpy(), rtol=2e-4, atol=2e-5)
+
+
+def test_pna_empty_segments_and_single_reductions():
+    # vertices 2 and 4 receive no edge: scatter leaves zeros, std = sqrt(1e-5)
+    ei = torch.tensor([[0, 1, 3, 3, 0], [1, 0, 0, 1, 3]], dtype=torch.int64)
+    N = 5
+    P = ops().pack(ei.to(DEV), N)
+    msg = torch.randn(5, 64)
+    msg_i = msg[P.perm.cpu().long()].to(DEV)
+    out = ops().pna_forward(msg_i, P.seg_off, N).cpu()
+    ref = gn_oracle.pna_aggregate(msg, ei[1], N)
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=1e-5, atol=2e-6)
+    assert torch.all(out[2, :192] == 0) and torch.all(out[4, :192] == 0)
+    for name in ('sum', 'mean', 'min', 'max', 'var', 'std'):
+        got = ops().segment_reduce(msg_i, P.seg_off, N, name).cpu()
+        want = gn_oracle.AGGREGATORS[name](msg, ei[1], N)
+        np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=2e-6)
+
+
+# ---- GN network forward -------------------------------------------------------------------------
+def run_forward(params, x, ei, ea, stash=False):
+    flat = util.flatten(params).to(DEV)
+    P = ops().pack(ei.to(DEV), x.shape[0])
+    ea_i = ops().permute_rows(ea.to(DEV), P.perm, True)
+    h, q, st = ops().gn_forward(flat, (2, 1, 0), P, x.to(DEV), ea_i, with_stash=stash)
+    return flat, P, ea_i, h, q, st
+
+
+@pytest.mark.parametrize('weights', ['init', 'trained'])
+def test_gn_forward_vs_oracle(weights):
+    rng = np.random.default_rng(4)
+    params = gn_oracle.init_params(seed=0) if weights == 'init' else util.load_parity_weights()
+    for gids in ([0], [11, 12, 13, 14], list(range(60, 76))):
+        _, x, ei, ea, _, _ = batch_of(gids, rng)
+        with torch.no_grad():
+            h_ref, q_ref = gn_oracle.gn_forward(params, x, ei, ea)
+        _, _, _, h, q, _ = run_forward(params, x, ei, ea)
+        # fp32 parity mode: same arithmetic, different summation order
+        tol = 2e-5 if weights == 'trained' else 1e-7
+        np.testing.assert_allclose(q.cpu().numpy(), q_ref.view(-1).numpy(), rtol=0, atol=tol)
+        np.testing.assert_allclose(h.cpu().numpy(), h_ref.numpy(), rtol=1e-4, atol=tol * 10)
+
+
+@pytest.mark.parametrize('tag', ['init', 'trained'])
+def test_gn_forward_vs_reference_golden(tag):
+    d = np.load(util.GOLD + '/gn_forward.npz')
+    params = gn_oracle.init_params(seed=0) if tag == 'init' else util.load_parity_weights()
+    o, qs = 0, []
+    obs, masks = [], []
+    for gi in d['graph_ids']:
+        g = GRAPHS[int(gi)]
+        col = d['colours'][o:o + g['n']].astype(np.int64)
+        o += g['n']
+        obs.append(gn_oracle.observation(g['adj'], col, g['edge_list']))
+        masks.append(col)
+    x, ei, ea = gn_oracle.collate(obs)                       # all 15 states as one batch
+    _, _, _, h, q, _ = run_forward(params, x, ei, ea)
+    tol = 2e-5 if tag == 'trained' else 1e-7
+    np.testing.assert_allclose(q.cpu().numpy(), d[tag + '_q'], rtol=0, atol=tol)
+    np.testing.assert_allclose(h.double().sum(1).cpu().numpy(), d[tag + '_h5_rowsum'], rtol=1e-4, atol=1e-4)
+    if tag == 'trained':
+        node_off = torch.tensor(np.concatenate([[0], np.cumsum([m.size for m in masks])]), dtype=torch.int32, device=DEV)
+        colour = torch.tensor(np.concatenate(masks), dtype=torch.int32, device=DEV)
+        act = ops().score_argmax(q, colour, node_off).cpu().numpy()
+        assert np.array_equal(act, d['trained_actions'])
+
+
+def test_gn_block_forward_returns_messages_in_internal_order():
+    rng = np.random.default_rng(5)
+    params = util.load_parity_weights()
+    _, x, ei, ea, _, _ = batch_of([8, 9], rng)
+    flat = util.flatten(params).to(DEV)
+    P = ops().pack(ei.to(DEV), x.shape[0])
+    ea_i = ops().permute_rows(ea.to(DEV), P.perm, True)
+    msg, upd = ops().gn_block_forward(flat, (2, 1, 0), 1, P, x.to(DEV), ea_i)
+    with torch.no_grad():
+        m_ref, u_ref = gn_oracle.gn_block(params, 1, x, ei, ea)
+    np.testing.assert_allclose(ops().permute_rows(msg, P.perm, False).cpu().numpy(), m_ref.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(upd.cpu().numpy(), u_ref.numpy(), rtol=1e-5, atol=2e-5)
+    # a middle block: 64-wide vertex and edge inputs
+    h1, e1 = u_ref, m_ref
+    msg2, upd2 = ops().gn_block_forward(flat, (2, 1, 0), 2, P, h1.to(DEV), ops().permute_rows(e1.to(DEV), P.perm, True))
+    with torch.no_grad():
+        m2, u2 = gn_oracle.gn_block(params, 2, h1, ei, e1)
+    np.testing.assert_allclose(ops().permute_rows(msg2, P.perm, False).cpu().numpy(), m2.numpy(), rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(upd2.cpu().numpy(), u2.numpy(), rtol=1e-5, atol=5e-5)
+
+
+# ---- backward -----------------------------------------------------------------------------------
+def oracle_grads(params, x, ei, ea, d_q, d_h, dtype):
+    pr = {k: v.clone().to(dtype).requires_grad_(True) for k, v in params.items()}
+    h, q = gn_oracle.gn_forward(pr, x.to(dtype), ei, ea.to(dtype))
+    loss = (q.view(-1) * d_q.to(dtype)).sum()
+    if d_h is not None:
+        loss = loss + (h * d_h.to(dtype)).sum()
+    loss.backward()
+    return torch.cat([pr[k].grad.reshape(-1) for k in params]).double().numpy()
+
+
+def grads_close(got, truth64, ref32, like, rtol=1e-4):
+    """Per parameter tensor.  The gradients are ill-conditioned in fp32 (the std aggregator
+    divides rounding noise by sqrt(1e-5) wherever a message column is constant), so the
+    yardstick is the reference arithmetic's own fp32 noise: our error against an fp64
+    evaluation must stay within 4x the fp32 oracle's error against the same fp64 evaluation,
+    plus rtol * max|grad|."""
+    o = 0
+    for k, v in like.items():
+        n = v.numel()
+        g, t, r = got[o:o + n].astype(np.float64), truth64[o:o + n], ref32[o:o + n]
+        o += n
+        scale = max(float(np.abs(t).max()), 1e-30)
+        noise = float(np.abs(r - t).max())
+        err = float(np.abs(g - t).max())
+        assert err <= 4 * noise + rtol * scale + 1e-9, (k, err, noise, scale)
+
+
+@pytest.mark.parametrize('weights', ['init', 'trained'])
+def test_gn_backward_vs_autograd(weights):
+    rng = np.random.default_rng(6)
+    params = gn_oracle.init_params(seed=1) if weights == 'init' else util.load_parity_weights()
+    _, x, ei, ea, _, _ = batch_of([2, 21, 43, 64, 85], rng)
+    N = x.shape[0]
+    torch.manual_seed(1)
+    d_q = torch.randn(N)
+    d_h = torch.randn(N, 64) * 0.1
+    flat, P, ea_i, h, q, st = run_forward(params, x, ei, ea, stash=True)
+    got_q = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV)).cpu().numpy()
+    grads_close(got_q, oracle_grads(params, x, ei, ea, d_q, None, torch.float64),
+                oracle_grads(params, x, ei, ea, d_q, None, torch.float32), params)
+    got_qh = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), d_h=d_h.to(DEV)).cpu().numpy()
+    grads_close(got_qh, oracle_grads(params, x, ei, ea, d_q, d_h, torch.float64),
+                oracle_grads(params, x, ei, ea, d_q, d_h, torch.float32), params)
+    got_h = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_h=d_h.to(DEV)).cpu().numpy()
+    grads_close(got_h, oracle_grads(params, x, ei, ea, d_q * 0, d_h, torch.float64),
+                oracle_grads(params, x, ei, ea, d_q * 0, d_h, torch.float32), params)
+    # accumulate=True adds on top
+    g2 = torch.from_numpy(got_q).to(DEV).clone()
+    ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), grad=g2, accumulate=True)
+    np.testing.assert_allclose(g2.cpu().numpy(), 2 * got_q, rtol=1e-3, atol=1e-6)
+
+
+def test_learn_step_vs_reference_golden():
+    """TD target, loss, gradients, Adam and the soft update against the unmodified reference's
+    DQNAgentGN.learn() (tests/golden/learn_step.npz)."""
+    d = np.load(util.GOLD + '/learn_step.npz')
+    pb = util.load_parity_weights()
+    gids = [int(g) for g in d['graph_ids']]
+    ns = [GRAPHS[g]['n'] for g in gids]
+    cur_cols = util.split_by(d['cur_colours'].astype(np.int64), ns)
+    nxt_cols = util.split_by(d['next_colours'].astype(np.int64), ns)
+    cur = gn_oracle.collate([gn_oracle.observation(GRAPHS[g]['adj'], c, GRAPHS[g]['edge_list']) for g, c in zip(gids, cur_cols)])
+    nxt = gn_oracle.collate([gn_oracle.observation(GRAPHS[g]['adj'], c, GRAPHS[g]['edge_list']) for g, c in zip(gids, nxt_cols)])
+    x, ei, ea = cur
+    flat_b = util.flatten(pb).to(DEV)
+    flat_t = torch.from_numpy(d['target_before']).to(DEV)
+    P = ops().pack(ei.to(DEV), x.shape[0])
+    ea_i = ops().permute_rows(ea.to(DEV), P.perm, True)
+    _, q_cur, st = ops().gn_forward(flat_b, (2, 1, 0), P, x.to(DEV), ea_i, with_stash=True)
+    _, q_next, _ = ops().gn_forward(flat_t, (2, 1, 0), P, nxt[0].to(DEV), ea_i)
+    node_off = torch.tensor(np.concatenate([[0], np.cumsum(ns)]), dtype=torch.int32, device=DEV)
+    next_colour = torch.tensor(d['next_colours'].astype(np.int32), device=DEV)
+    loss, q_exp, q_tgt, d_q = ops().td_target_loss(
+        q_cur, q_next, next_colour, node_off, torch.tensor(d['actions'], dtype=torch.int32, device=DEV),
+        torch.tensor(d['rewards'], device=DEV), torch.tensor(d['dones'], dtype=torch.int32, device=DEV), 1.0)
+    np.testing.assert_allclose(q_exp.cpu().numpy(), d['q_expected'], atol=2e-5)
+    np.testing.assert_allclose(q_tgt.cpu().numpy(), d['q_targets'], atol=2e-5)
+    assert abs(float(loss.item()) - float(d['loss'])) < 1e-5
+    grad = ops().gn_backward(flat_b, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q)
+    truth = oracle_grads(pb, x, ei, ea, d_q.cpu(), None, torch.float64)
+    grads_close(grad.cpu().numpy(), truth, d['grads'].astype(np.float64), pb)
+    m = torch.zeros_like(flat_b)
+    v = torch.zeros_like(flat_b)
+    ops().adam_soft_update(flat_b, grad, m, v, flat_t, 1, lr=1e-3, tau=1e-3)
+    diff = np.abs(flat_b.cpu().numpy() - d['behaviour_after'])
+    assert np.mean(diff > 1e-6) < 1e-3           # first Adam step = lr*sign(g): flips only where g ~ 0
+    np.testing.assert_allclose(flat_t.cpu().numpy(), d['target_after'], atol=3e-6)
+
+
+def test_adam_and_soft_update_bitwise_vs_torch():
+    torch.manual_seed(3)
+    n = 198529
+    p = torch.randn(n)
+    t = torch.randn(n)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    pd, td = p.to(DEV), t.to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ref_t = t.clone()
+    for step in range(1, 4):
+        g = torch.randn(n) * 10 ** (-step)
+        ref_p.grad = g.clone()
+        opt.step()
+        ref_t = 1e-3 * ref_p.detach() + (1.0 - 1e-3) * ref_t
+        ops().adam_soft_update(pd, g.to(DEV), m, v, td, step, lr=1e-3, tau=1e-3)
+        np.testing.assert_allclose(pd.cpu().numpy(), ref_p.detach().numpy(), rtol=0, atol=2e-7)
+        np.testing.assert_allclose(td.cpu().numpy(), ref_t.numpy(), rtol=0, atol=2e-7)
+    b = torch.randn(1000, device=DEV)
+    tt = torch.randn(1000, device=DEV)
+    want = 0.25 * b + (1.0 - 0.25) * tt
+    ops().soft_update(b, tt, 0.25)
+    assert torch.equal(tt, want)
+    ops().soft_update(b, tt, 1.0)               # dqn_agent.py:100 hard copy
+    assert torch.equal(tt, b)
+
+
+def test_td_target_vs_oracle_with_done_and_masks():
+    rng = np.random.default_rng(7)
+    ns = [5, 1, 17, 33]
+    node_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    N = int(node_off[-1])
+    q_cur = rng.standard_normal(N).astype(np.float32)
+    q_next = rng.standard_normal(N).astype(np.float32)
+    assigned = (rng.random(N) < 0.5).astype(np.int64)
+    assigned[node_off[1]] = 1                           # the 1-vertex graph is finished
+    assigned[node_off[2]:node_off[3]] = 1
+    assigned[node_off[2] + 3] = 0
+    dones = np.asarray([0, 1, 0, 0], dtype=np.int32)
+    actions = np.asarray([2, 0, 16, 7], dtype=np.int32)
+    rewards = np.asarray([-1, 0, 0, -1], dtype=np.float32)
+    want = gn_oracle.td_targets(q_next, assigned, ns, rewards, dones, gamma=1.0)
+    colour = torch.tensor(np.where(assigned == 1, 0, -1).astype(np.int32), device=DEV)
+    loss, q_exp, q_tgt, d_q = ops().td_target_loss(
+        torch.tensor(q_cur, device=DEV), torch.tensor(q_next, device=DEV), colour, torch.tensor(node_off, device=DEV),
+        torch.tensor(actions, device=DEV), torch.tensor(rewards, device=DEV), torch.tensor(dones, device=DEV), 1.0)
+    assert np.array_equal(q_tgt.cpu().numpy(), want)
+    qe = q_cur[node_off[:-1] + actions]
+    assert np.array_equal(q_exp.cpu().numpy(), qe)
+    np.testing.assert_allclose(float(loss.item()), float(np.mean((qe - want) ** 2)), rtol=1e-6)
+    dq = np.zeros(N, dtype=np.float32)
+    dq[node_off[:-1] + actions] = 2 * (qe - want) / 4
+    np.testing.assert_allclose(d_q.cpu().numpy(), dq, rtol=1e-6, atol=0)
+
+
+# ---- environment: bit-exact ----------------------------------------------------------------------
+class DeviceEnv(object):
+    def __init__(self, gids):
+        self.adj, self.adj_off, self.node_off, self.N, self.E = dense_inputs(gids)
+        G = len(gids)
+        self.colour = torch.empty(self.N, dtype=torch.int32, device=DEV)
+        self.max_colour = torch.empty(G, dtype=torch.int32, device=DEV)
+        self.reward = torch.zeros(G, device=DEV)
+        self.done = torch.zeros(G, dtype=torch.int32, device=DEV)
+        self.x = torch.empty(self.N, 2, device=DEV)
+        ops().env_reset(self.colour, self.max_colour, self.x, self.node_off)
+
+    def step(self, actions):
+        a = torch.tensor(actions, dtype=torch.int32, device=DEV)
+        ops().env_step(self.adj, self.adj_off, self.node_off, a, self.colour, self.max_colour, self.reward, self.done, self.x)
+
+
+def test_env_traces_bit_exact_batched():
+    """All 34 golden episodes of the reference env advance in lock-step as ONE device batch."""
+    d = np.load(util.GOLD + '/env_traces.npz')
+    gids = [int(g) for g in d['graph_ids']]
+    acts = util.split_by(d['actions'], d['steps'])
+    rews = util.split_by(d['rewards'], d['steps'])
+    dones = util.split_by(d['dones'], d['steps'])
+    ns = [GRAPHS[g]['n'] for g in gids]
+    cols, o = [], 0
+    for n, s in zip(ns, d['steps']):
+        cols.append(d['colours'][o:o + n * int(s)].reshape(int(s), n))
+        o += n * int(s)
+    env = DeviceEnv(gids)
+    x0 = env.x.cpu().numpy()
+    assert np.all(x0[:, 1] == -1)
+    assert np.array_equal(x0[:, 0], np.concatenate([np.arange(n) for n in ns]))
+    node_off = env.node_off.cpu().numpy()
+    for t in range(int(d['steps'].max())):
+        a = [int(acts[i][t]) if t < len(acts[i]) else -1 for i in range(len(gids))]
+        env.step(a)
+        col = env.colour.cpu().numpy()
+        r = env.reward.cpu().numpy()
+        dn = env.done.cpu().numpy()
+        xx = env.x.cpu().numpy()
+        assert np.array_equal(xx[:, 1].astype(np.int64), col)
+        for i in range(len(gids)):
+            tt = min(t, len(acts[i]) - 1)
+            assert np.array_equal(col[node_off[i]:node_off[i + 1]], cols[i][tt]), (i, t)
+            if t < len(acts[i]):
+                assert r[i] == rews[i][t] and dn[i] == dones[i][t]
+            else:
+                assert r[i] == 0 and dn[i] == 1
+    assert np.array_equal(env.max_colour.cpu().numpy() + 1, [c[-1].max() + 1 for c in cols])
+
+
+def test_env_dsatur_known_answers_all_100():
+    gids = list(range(100))
+    env = DeviceEnv(gids)
+    T = max(len(GRAPHS[g]['dsatur_order']) for g in gids)
+    for t in range(T):
+        env.step([int(GRAPHS[g]['dsatur_order'][t]) if t < len(GRAPHS[g]['dsatur_order']) else -1 for g in gids])
+    assert torch.all(env.done == 1)
+    assert np.array_equal(env.max_colour.cpu().numpy() + 1, [GRAPHS[g]['dsatur_colours'] for g in gids])
+
+
+def test_env_first_vertex_and_distance_counts():
+    gids = list(range(100))
+    adj, adj_off, node_off, N, E = dense_inputs(gids)
+    act, counts = ops().env_first_vertex(adj, adj_off, node_off, N, want_counts=True)
+    want_counts = np.concatenate([GRAPHS[g]['dist_counts'] for g in gids])
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want_counts)
+    assert np.array_equal(act.cpu().numpy(), [env_oracle.first_vertex(GRAPHS[g]['adj']) for g in gids])
+
+
+def test_score_argmax_ties_and_empty():
+    q = torch.tensor([1., 5., 5., 2., 9., 3., 3.], device=DEV)
+    colour = torch.tensor([-1, -1, -1, 0, 0, 1, 2], dtype=torch.int32, device=DEV)
+    node_off = torch.tensor([0, 3, 5, 7], dtype=torch.int32, device=DEV)
+    act, qb = ops().score_argmax(q, colour, node_off, want_q=True)
+    assert act.cpu().tolist() == [1, -1, -1]
+    assert qb.cpu()[0] == 5 and torch.isinf(qb.cpu()[1])
