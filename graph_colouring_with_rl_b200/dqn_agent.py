@@ -1,0 +1,196 @@
+"""Drop-in for the reference's dqn_agent.py: `ReplayBuffer` and `DQNAgentGN` with the same
+constructor arguments, hyper-parameter fields and method signatures; act / learn run on the
+device through libgcrl_b200.
+
+Reference: dqn_agent.py:8-65 (ReplayBuffer), :68-238 (DQNAgentGN).
+
+Differences that are deliberate and invisible to callers:
+  * `learn()` makes no per-graph Python loops and no host round trips: two batched forwards,
+    `gcrl_td_target_loss`, `gcrl_gn_backward`, and one fused Adam + soft-update launch;
+  * the replay buffer keeps each transition's tensors where they already are (device tensors
+    from the device environment stay on the device; the reference forces `.cpu()`), and when a
+    transition carries a dense adjacency (`ColouringData`) the minibatch is batched straight
+    from adjacency bytes with `gcrl_pack_dense` instead of concatenating edge lists;
+  * random numbers are drawn from the same generators in the same order (`random.random`,
+    `random.choice`, `np.random.choice`) so seeded runs take the same branches.
+"""
+import random
+
+import numpy as np
+import torch
+
+from . import ops
+from .architecture import GNNetwork
+from .data import Batch
+
+
+class ReplayBuffer(object):
+    def __init__(self, max_size, global_features_size):
+        self.max_mem_size = max_size
+        self.current_mem_size = 0
+        self.data_memory = [None] * self.max_mem_size
+        self.current_global_features = np.zeros((self.max_mem_size, global_features_size), dtype=np.float32)
+        self.assigned_vertices_memory = np.zeros(self.max_mem_size, dtype=object)
+        self.action_ind_memory = np.zeros((self.max_mem_size, 1))
+        self.reward_memory = np.zeros(self.max_mem_size)
+        self.next_data_memory = [None] * self.max_mem_size
+        self.next_global_features = np.zeros((self.max_mem_size, global_features_size), dtype=np.float32)
+        self.done_memory = np.zeros(self.max_mem_size, dtype=np.intc)
+
+    def store_transition(self, data, current_global_features, assigned_vertices, action_ind, reward, next_data,
+                         next_global_features, done):
+        index = self.current_mem_size % self.max_mem_size          # dqn_agent.py:33
+        self.data_memory[index] = data
+        self.current_global_features[index] = current_global_features
+        self.assigned_vertices_memory[index] = assigned_vertices
+        self.action_ind_memory[index] = action_ind
+        self.reward_memory[index] = reward
+        self.next_data_memory[index] = next_data
+        self.next_global_features[index] = next_global_features
+        self.done_memory[index] = done
+        self.current_mem_size += 1
+
+    def sample_indices(self, sample_size):
+        max_mem = min(self.current_mem_size, self.max_mem_size)
+        return np.random.choice(max_mem, sample_size)              # with replacement (:48)
+
+    def sample_buffer(self, sample_size):
+        """Same 8-tuple as the reference (:45-65)."""
+        batch = self.sample_indices(sample_size)
+        return self.gather(batch)
+
+    def gather(self, batch):
+        datas_batch = Batch.from_data_list([self.data_memory[i] for i in batch])
+        next_datas_batch = Batch.from_data_list([self.next_data_memory[i] for i in batch])
+        return (datas_batch, self.current_global_features[batch], self.assigned_vertices_memory[batch],
+                self.action_ind_memory[batch], self.reward_memory[batch], next_datas_batch,
+                self.next_global_features[batch], self.done_memory[batch])
+
+
+class DQNAgentGN():
+    def __init__(self, len_vertex_features, len_edge_features, len_global_features, test_mode=False,
+                 math_mode='fp32'):
+        self.gamma = 1                 # dqn_agent.py:80-88
+        self.alpha = 1e-3
+        self.tau = 1e-3
+        self.no_episodes = 25000
+        self.eps_start = .9
+        self.eps_end = .01
+        self.max_buffer_size = int(1e5)
+        self.batch_size = 64
+        self.update_every = 5
+        self.len_global_features = len_global_features
+        self.learn_counter = 0
+        self.gn_behaviour = GNNetwork(len_vertex_features, len_edge_features, len_global_features, name='GN',
+                                      alpha=self.alpha, math_mode=math_mode)
+        if not test_mode:
+            self.gn_target = GNNetwork(len_vertex_features, len_edge_features, len_global_features,
+                                       name='GN_target', alpha=self.alpha, math_mode=math_mode)
+            self.soft_update(self.gn_behaviour, self.gn_target, 1)
+            self.memory = ReplayBuffer(self.max_buffer_size, len_global_features)
+        self.episode_no = 0
+        self.last_loss = None          # device scalar of the most recent learn() (not in the reference)
+
+    # ---- act (dqn_agent.py:108-140) ---------------------------------------------------------------
+    def choose_action(self, data, global_features, unassigned_vertices, epsilon=None, test_mode=False):
+        if epsilon is None:
+            if test_mode:
+                epsilon = 0
+            else:
+                epsilon_decay = (self.eps_end / self.eps_start) ** (1 / self.no_episodes)
+                epsilon = self.eps_start * (epsilon_decay ** self.episode_no)
+        if random.random() > epsilon:
+            net = self.gn_behaviour
+            gn_input = data.to(net.device)
+            n = gn_input.x.shape[0]
+            gf = torch.tensor(global_features, dtype=torch.float).unsqueeze(0).to(net.device)
+            with torch.no_grad():
+                _, action_values = net(gn_input, gf, [0] * n, None)
+            # masked first-argmax on the device (== np.argmax over the ascending unassigned list)
+            mask = np.zeros(n, dtype=np.int32)
+            mask[np.asarray(unassigned_vertices, dtype=np.int64)] = -1
+            colour = torch.from_numpy(mask).to(net.device)
+            node_off = torch.tensor([0, n], dtype=torch.int32, device=net.device)
+            vertex_ind = int(ops.score_argmax(action_values.view(-1), colour, node_off).item())
+        else:
+            vertex_ind = random.choice(unassigned_vertices)
+        return vertex_ind
+
+    def remember(self, data, current_global_features, assigned_vertices, action_ind, reward, next_data,
+                 next_global_features, done):
+        self.memory.store_transition(data, current_global_features, assigned_vertices, action_ind, reward,
+                                     next_data, next_global_features, done)
+
+    # ---- learn (dqn_agent.py:147-223) ---------------------------------------------------------------
+    def _collate(self, datas, device):
+        """-> (packed, eattr internal, x [N,vd], node_off int32 [G+1])."""
+        ns = [int(d.x.shape[0]) for d in datas]
+        node_off = torch.tensor(np.concatenate([[0], np.cumsum(ns)]), dtype=torch.int32, device=device)
+        x = torch.cat([d.x.to(device, torch.float32) for d in datas], 0)
+        if all(getattr(d, 'adj', None) is not None for d in datas):
+            adj = torch.cat([d.adj.to(device).reshape(-1) for d in datas])
+            nn_ = np.asarray(ns, dtype=np.int64)
+            adj_off = torch.tensor(np.concatenate([[0], np.cumsum(nn_ * nn_)[:-1]]), dtype=torch.int64, device=device)
+            packed, eattr = ops.pack_dense(adj, adj_off, node_off, int(nn_.sum()), int((nn_ * (nn_ - 1)).sum()))
+            return packed, eattr, x, node_off
+        b = Batch.from_data_list([d if d.x.device == d.edge_index.device else d.to(device) for d in datas])
+        ei = b.edge_index.to(device)
+        packed = ops.pack(ei, x.shape[0])
+        eattr = ops.permute_rows(b.edge_attr.to(device, torch.float32).reshape(ei.shape[1], -1), packed.perm, True)
+        return packed, eattr, x, node_off
+
+    def learn(self):
+        if self.memory.current_mem_size < 10 * self.batch_size:
+            return
+        if self.learn_counter == 0:
+            print('Starting learning')
+            self.learn_counter += 1
+        mem = self.memory
+        batch = mem.sample_indices(self.batch_size)
+        self.learn_on(batch)
+
+    def learn_on(self, batch):
+        """One DQN step on the replay slots `batch` (what learn() does after sampling)."""
+        mem = self.memory
+        net_b, net_t = self.gn_behaviour, self.gn_target
+        dev = net_b.device
+        cur = [mem.data_memory[i] for i in batch]
+        nxt = [mem.next_data_memory[i] for i in batch]
+        packed, eattr, x_cur, node_off = self._collate(cur, dev)
+        x_next = torch.cat([d.x.to(dev, torch.float32) for d in nxt], 0)
+        # assigned-after-step one-hot (dqn_main.py:184) -> "colour >= 0 means assigned"
+        assigned = np.concatenate([np.asarray(mem.assigned_vertices_memory[i]).reshape(-1) for i in batch])
+        next_colour = torch.from_numpy(np.where(assigned == 1, 0, -1).astype(np.int32)).to(dev)
+        action = torch.from_numpy(mem.action_ind_memory[batch].reshape(-1).astype(np.int32)).to(dev)
+        reward = torch.from_numpy(mem.reward_memory[batch].astype(np.float32)).to(dev)
+        done = torch.from_numpy(mem.done_memory[batch].astype(np.int32)).to(dev)
+        gfeat = gfeat_n = vgraph = None
+        if self.len_global_features > 0:
+            gfeat = torch.from_numpy(mem.current_global_features[batch]).to(dev)
+            gfeat_n = torch.from_numpy(mem.next_global_features[batch]).to(dev)
+            counts = (node_off[1:] - node_off[:-1]).long()
+            vgraph = torch.repeat_interleave(torch.arange(len(batch), device=dev), counts).int()
+        flat_b, flat_t = net_b.flat_params(), net_t.flat_params()
+        _, q_cur, stash = ops.gn_forward(flat_b, net_b.dims, packed, x_cur, eattr, gfeat, vgraph, with_stash=True,
+                                         math_mode=net_b.math_mode)
+        _, q_next, _ = ops.gn_forward(flat_t, net_t.dims, packed, x_next, eattr, gfeat_n, vgraph,
+                                      math_mode=net_t.math_mode)
+        loss, q_exp, q_tgt, d_q = ops.td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done,
+                                                     self.gamma)
+        if net_b._flat_grad is None:
+            net_b._flat_grad = torch.zeros_like(flat_b)
+        grad = ops.gn_backward(flat_b, net_b.dims, packed, x_cur, eattr, stash, d_q=d_q, gfeat=gfeat, vgraph=vgraph,
+                               grad=net_b._flat_grad, accumulate=False, math_mode=net_b.math_mode)
+        # optimizer.step() and soft_update(behaviour, target, tau) fused (dqn_agent.py:220,223)
+        net_b.optimizer.step(target_flat=flat_t, tau=self.tau, grad=grad)
+        self.last_loss = loss
+        return loss
+
+    def soft_update(self, behaviour_network, target_network, tau):
+        ops.soft_update(behaviour_network.flat_params(), target_network.flat_params(), tau)
+
+    def save_models(self, checkpoint_filepath_root):
+        return self.gn_behaviour.save_checkpoint(checkpoint_filepath_root)
+
+    def load_models(self, checkpoint_filepath_root):
+        self.gn_behaviour.load_checkpoint(checkpoint_filepath_root)
