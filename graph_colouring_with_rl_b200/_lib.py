@@ -29,6 +29,9 @@ SIGNATURES = {
     'gcrl_last_error': (ctypes.c_char_p, []),
     'gcrl_version': (c_int, []),
     'gcrl_sm_count': (c_int, []),
+    'gcrl_launch_count': (c_int64, []),
+    'gcrl_prof_enable': (c_int, [c_int]),
+    'gcrl_prof_read': (c_int, [P, P, c_int]),
     'gcrl_param_layout': (c_int, [c_int, c_int, c_int, P]),
     'gcrl_pack_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'gcrl_pack': (c_int, [P, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),

@@ -13,6 +13,9 @@ namespace gcrl {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+void count_launch(int n);                       // prof.cu: kernels launched by the library
+int prof_begin(int kind, cudaStream_t st);      // prof.cu: event timing when enabled, else -1
+void prof_end(int token, cudaStream_t st);
 
 #define GCRL_CHECK_ARG(cond)                                                          \
     do {                                                                              \
@@ -32,7 +35,11 @@ int sm_count();
         }                                                                             \
     } while (0)
 
-#define GCRL_LAUNCH_CHECK() GCRL_CUDA(cudaGetLastError())
+#define GCRL_LAUNCH_CHECK()              \
+    do {                                 \
+        gcrl::count_launch(1);           \
+        GCRL_CUDA(cudaGetLastError());   \
+    } while (0)
 
 // ---- flat parameter layout (state_dict order, architecture.py:157-167) -----------------
 struct BlockW {

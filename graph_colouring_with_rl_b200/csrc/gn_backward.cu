@@ -503,8 +503,10 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
     int64_t tiles = ((int64_t)a.E + TILE - 1) / TILE;
     int64_t grid = sm_count();
     if (grid > tiles) grid = tiles;
+    const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (a.m ? GCRL_PROF_EDGE_BWD : GCRL_PROF_EDGE_BWD_LAST), st);
     if (first) k_edge_bwd<true><<<(int)grid, 256, sizeof(EdgeBwdSmem), st>>>(a);
     else k_edge_bwd<false><<<(int)grid, 256, sizeof(EdgeBwdSmem), st>>>(a);
+    prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -397,8 +397,10 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
     int64_t items = (E + ITEM_EDGES - 1) / ITEM_EDGES;
     int64_t grid = (int64_t)sm_count() * 2;
     if (grid > items) grid = items;
+    const int tok = prof_begin(first ? GCRL_PROF_EDGE_FWD_FIRST : (m_out ? GCRL_PROF_EDGE_FWD : GCRL_PROF_EDGE_FWD_LAST), st);
     if (first) k_edge_fwd<true><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
     else k_edge_fwd<false><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
+    prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -251,6 +251,7 @@ int gcrl_pack(const int64_t* ei, int64_t E, int64_t N, int32_t* seg_off, int32_t
         // edges with invalid ids are dropped (err flag set); ranking walks only the
         // seg_off[N] valid slots, a bound it reads on the device.
         k_rank_in_segment<<<blocks, threads, 0, st>>>(ei, E, seg_off, tmp, N, src, dst, perm);
+        count_launch(3);
     }
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -280,6 +281,7 @@ int gcrl_pack_dense(const uint8_t* adj, const int64_t* adj_off, const int32_t* n
         if (blocks > sm_count() * 32) blocks = sm_count() * 32;
         k_pack_dense<<<blocks, 256, 0, st>>>(adj, adj_off, node_off, eoff, G, N, seg_off, src, dst,
                                              perm, eattr);
+        count_launch(G > 0 ? 2 : 1);
     }
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;

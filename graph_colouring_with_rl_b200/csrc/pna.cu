@@ -225,6 +225,7 @@ int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t N, int64_
     if (N == 0) return GCRL_OK;
     GCRL_CHECK_ARG(seg_off && out && (E == 0 || msg));
     cudaStream_t st = (cudaStream_t)stream;
+    const int tok = prof_begin(GCRL_PROF_PNA_FWD, st);
     if (F == 64 && (((uintptr_t)msg | (uintptr_t)out) & 15) == 0) {
         // 8 warps per CTA; enough CTAs for >= 2 waves at 8 CTAs/SM, capped (grid-stride)
         int64_t blocks = (N + 7) / 8;
@@ -238,6 +239,7 @@ int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t N, int64_
         if (blocks > cap) blocks = cap;
         k_pna_fwd_generic<<<(int)blocks, 256, 0, st>>>(msg, seg_off, N, F, out, arg_min, arg_max, var_out);
     }
+    prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -253,8 +255,10 @@ int gcrl_pna_backward(const float* msg, const float* out, const float* var, cons
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
+    const int tok = prof_begin(GCRL_PROF_PNA_BWD, (cudaStream_t)stream);
     k_pna_bwd<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(msg, out, var, d_out, seg_off, dst,
                                                               arg_min, arg_max, E, F, d_msg);
+    prof_end(tok, (cudaStream_t)stream);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -1,0 +1,174 @@
+"""Large-minibatch DQN learning over complete-graph transitions (device-resident
+replay data).  A `TransitionBatch` holds G transitions as flat arrays -- dense adjacency
+bytes, colour vectors before/after the step, action, reward, done -- i.e. what
+dqn_agent.py:147-223 consumes, without per-transition Python objects.  `QLearner` runs the
+learn step over it in micro-batches sized to fit HBM (the edge state of 4096 graphs x 200
+vertices is 41.7 GB per fp32 [E,64] tensor), accumulating one flat gradient, which at
+world_size > 1 is summed with a single NCCL all-reduce (794 KB) before the fused Adam.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+FIELDS = ('adj', 'cur_colour', 'next_colour', 'action', 'reward', 'done')
+
+
+class TransitionBatch(object):
+    def __init__(self, ns, adj, cur_colour, next_colour, action, reward, done):
+        """ns: host int64 [G] vertex counts; the rest are device tensors
+        (adj uint8 [sum n^2], colours int32 [N], action int32 [G], reward f32 [G], done int32 [G])."""
+        self.ns = np.asarray(ns, dtype=np.int64)
+        self.adj, self.cur_colour, self.next_colour = adj, cur_colour, next_colour
+        self.action, self.reward, self.done = action, reward, done
+        dev = adj.device
+        self.device = dev
+        self.n_graphs = int(self.ns.size)
+        self.node_off_h = np.concatenate([[0], np.cumsum(self.ns)]).astype(np.int64)
+        self.adj_off_h = np.concatenate([[0], np.cumsum(self.ns * self.ns)]).astype(np.int64)
+        self.edge_off_h = np.concatenate([[0], np.cumsum(self.ns * (self.ns - 1))]).astype(np.int64)
+        self.n_vertices = int(self.node_off_h[-1])
+        self.n_edges = int(self.edge_off_h[-1])
+        self.node_off = torch.from_numpy(self.node_off_h.astype(np.int32)).to(dev)
+        self.adj_off = torch.from_numpy(self.adj_off_h[:-1].copy()).to(dev)
+        counts = torch.from_numpy(self.ns).to(dev)
+        start = torch.repeat_interleave(self.node_off[:-1].long(), counts)
+        self.names = (torch.arange(self.n_vertices, device=dev) - start).float()   # x[:,0] (graph_colouring_env.py:124-128)
+
+    @classmethod
+    def from_host(cls, ns, host, device):
+        """host: dict of (ideally pinned) CPU tensors named like FIELDS; async H2D copies."""
+        dev = torch.device(device)
+        t = {k: host[k].to(dev, non_blocking=True) for k in FIELDS}
+        return cls(ns, t['adj'], t['cur_colour'], t['next_colour'], t['action'], t['reward'], t['done'])
+
+    @staticmethod
+    def host_bytes(host):
+        return int(sum(host[k].numel() * host[k].element_size() for k in FIELDS))
+
+    def x_of(self, colour, v0=0, v1=None):
+        """Observation x = [vertex name, colour] of vertices [v0, v1) given their colours."""
+        v1 = self.n_vertices if v1 is None else v1
+        return torch.stack([self.names[v0:v1], colour.float()], 1)
+
+    def micro_ranges(self, max_edges):
+        """Contiguous graph ranges whose complete edge count stays within max_edges."""
+        out, g0 = [], 0
+        while g0 < self.n_graphs:
+            g1 = g0 + 1
+            while g1 < self.n_graphs and self.edge_off_h[g1 + 1] - self.edge_off_h[g0] <= max_edges:
+                g1 += 1
+            out.append((g0, g1))
+            g0 = g1
+        return out
+
+
+class _Slice(object):
+    """Views of one micro-batch [g0, g1) of a TransitionBatch."""
+
+    def __init__(self, b, g0, g1):
+        v0, v1 = int(b.node_off_h[g0]), int(b.node_off_h[g1])
+        a0, a1 = int(b.adj_off_h[g0]), int(b.adj_off_h[g1])
+        self.v0, self.v1, self.g0, self.g1 = v0, v1, g0, g1
+        self.n_vertices = v1 - v0
+        self.n_edges = int(b.edge_off_h[g1] - b.edge_off_h[g0])
+        self.adj = b.adj[a0:a1]
+        self.adj_off = b.adj_off[g0:g1] - a0
+        self.node_off = b.node_off[g0:g1 + 1] - v0
+        self.packed, self.eattr = ops.pack_dense(self.adj, self.adj_off, self.node_off, self.n_vertices, self.n_edges)
+
+
+class QLearner(object):
+    def __init__(self, agent, max_edges_per_micro_batch=512 * 200 * 199, process_group=None):
+        self.agent = agent
+        self.max_edges = int(max_edges_per_micro_batch)
+        self.group = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._stash = None
+
+    @torch.no_grad()
+    def target_q(self, batch):
+        """Target-network Q of every vertex of the next states (dqn_agent.py:187-188) -> [N]."""
+        net = self.agent.gn_target
+        flat = net.flat_params()
+        out = torch.empty(batch.n_vertices, dtype=torch.float32, device=batch.device)
+        for g0, g1 in batch.micro_ranges(self.max_edges):
+            s = _Slice(batch, g0, g1)
+            x = batch.x_of(batch.next_colour[s.v0:s.v1], s.v0, s.v1)
+            _, q, _ = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, math_mode=net.math_mode)
+            out[s.v0:s.v1] = q
+        return out
+
+    @torch.no_grad()
+    def fwd_bwd(self, batch, q_next):
+        """Behaviour forward, TD loss against q_next, backward.  Leaves the (all-reduced) mean
+        gradient in the behaviour net's flat gradient buffer and returns the loss [1]."""
+        agent = self.agent
+        net = agent.gn_behaviour
+        flat = net.flat_params()
+        if net._flat_grad is None:
+            net._flat_grad = torch.zeros_like(flat)
+        grad = net._flat_grad
+        total = batch.n_graphs * self.world
+        loss = torch.zeros(1, dtype=torch.float32, device=batch.device)
+        first = True
+        for g0, g1 in batch.micro_ranges(self.max_edges):
+            s = _Slice(batch, g0, g1)
+            x = batch.x_of(batch.cur_colour[s.v0:s.v1], s.v0, s.v1)
+            _, q, self._stash = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, with_stash=True,
+                                               math_mode=net.math_mode, stash=self._stash)
+            l, _, _, d_q = ops.td_target_loss(q, q_next[s.v0:s.v1], batch.next_colour[s.v0:s.v1], s.node_off,
+                                              batch.action[g0:g1], batch.reward[g0:g1], batch.done[g0:g1],
+                                              agent.gamma, batch_total=total)
+            loss += l
+            ops.gn_backward(flat, net.dims, s.packed, x, s.eattr, self._stash, d_q=d_q, grad=grad,
+                            accumulate=not first, math_mode=net.math_mode)
+            first = False
+        if self.world > 1:
+            torch.distributed.all_reduce(grad, group=self.group)        # sum of per-rank (1/B_global)-scaled grads
+            torch.distributed.all_reduce(loss, group=self.group)
+        return loss
+
+    @torch.no_grad()
+    def learn_step(self, batch):
+        """dqn_agent.py:147-223 on a TransitionBatch: target forward, behaviour forward/backward,
+        fused Adam + soft target update."""
+        agent = self.agent
+        q_next = self.target_q(batch)
+        loss = self.fwd_bwd(batch, q_next)
+        agent.gn_behaviour.optimizer.step(target_flat=agent.gn_target.flat_params(), tau=agent.tau,
+                                          grad=agent.gn_behaviour._flat_grad)
+        agent.last_loss = loss
+        return loss
+
+
+@torch.no_grad()
+def synthetic_transitions(adjs, frac_coloured, seed, device):
+    """Mid-episode transitions on the given graphs: colour about frac_coloured of each
+    graph's vertices in uniformly random order through the device environment, then take one
+    more random action and record (s, a, r, s', done).  Returns (ns, dict of CPU tensors)."""
+    from .envs import BatchedColouringEnv
+    env = BatchedColouringEnv(adjs, device=device)
+    gen = torch.Generator(device=env.device)
+    gen.manual_seed(seed)
+
+    def random_actions(active):
+        r = torch.rand(env.n_vertices, generator=gen, device=env.device)
+        a = ops.score_argmax(r, env.colour, env.node_off)
+        return torch.where(active, a, torch.full_like(a, -1))
+    steps = int(frac_coloured * int(env.ns.max()))
+    target = torch.from_numpy((frac_coloured * env.ns).astype(np.int64)).to(env.device)
+    counts = torch.from_numpy(env.ns).to(env.device)
+    gid = torch.repeat_interleave(torch.arange(env.n_graphs, device=env.device), counts)
+    for _ in range(steps):
+        coloured = torch.zeros(env.n_graphs, dtype=torch.long, device=env.device).index_add_(0, gid, (env.colour >= 0).long())
+        uncol = counts - coloured
+        env.step(random_actions((coloured < target) & (uncol > 1)))
+    cur = env.colour.clone()
+    act = random_actions(torch.ones(env.n_graphs, dtype=torch.bool, device=env.device))
+    env.step(act)
+    host = dict(adj=env.adj.cpu(), cur_colour=cur.cpu(), next_colour=env.colour.cpu(), action=act.cpu(),
+                reward=env.reward.cpu(), done=env.done.cpu())
+    return env.ns.copy(), host

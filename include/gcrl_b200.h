@@ -55,6 +55,24 @@ int gcrl_version(void);
 /* number of SMs of the current device (grid sizing) */
 int gcrl_sm_count(void);
 
+/* ---- instrumentation ---------------------------------------------------------------------
+ * gcrl_launch_count: kernels this library has launched since it was loaded.
+ * gcrl_prof_enable(1): bracket every launch of the dominant kernels with CUDA events on the
+ * launch stream; gcrl_prof_read syncs on them and returns, per kind, total milliseconds and
+ * launch count since the last read (then resets). */
+#define GCRL_PROF_EDGE_FWD_FIRST 0  /* block 1: reads edge_attr, writes e_1 */
+#define GCRL_PROF_EDGE_FWD 1        /* blocks 2-4: reads e_{l-1}, writes e_l */
+#define GCRL_PROF_EDGE_FWD_LAST 2   /* block 5: reads e_4, writes nothing per edge */
+#define GCRL_PROF_EDGE_BWD_FIRST 3  /* block 1: reads e_1, d e_1 */
+#define GCRL_PROF_EDGE_BWD 4        /* blocks 2-4: reads e_{l-1}, e_l, d e_l; writes d e_{l-1} */
+#define GCRL_PROF_EDGE_BWD_LAST 5   /* block 5: reads e_4; writes d e_4 */
+#define GCRL_PROF_PNA_FWD 6
+#define GCRL_PROF_PNA_BWD 7
+#define GCRL_PROF_KINDS 8
+int64_t gcrl_launch_count(void);
+int gcrl_prof_enable(int on);
+int gcrl_prof_read(double* ms, int64_t* launches, int n_kinds);
+
 /* ---- parameter layout ------------------------------------------------------------------
  * One flat fp32 buffer in state_dict order (architecture.py:157-167): for block l=1..5
  * message_mlp.0.{weight,bias}, message_mlp.2.{weight,bias}, update_mlp.0.{weight,bias},

@@ -216,7 +216,9 @@ def test_gn_block_forward_returns_messages_in_internal_order():
 
 
 # ---- backward -----------------------------------------------------------------------------------
-def oracle_grads(params, x, ei, ea, d_q, d_h, dtype):
+def oracle_grads(params, x, ei, ea, d_q, d_h, dtype, perm=None):
+    if perm is not None:
+        ei, ea = ei[:, perm], ea[perm]
     pr = {k: v.clone().to(dtype).requires_grad_(True) for k, v in params.items()}
     h, q = gn_oracle.gn_forward(pr, x.to(dtype), ei, ea.to(dtype))
     loss = (q.view(-1) * d_q.to(dtype)).sum()
@@ -226,27 +228,32 @@ def oracle_grads(params, x, ei, ea, d_q, d_h, dtype):
     return torch.cat([pr[k].grad.reshape(-1) for k in params]).double().numpy()
 
 
-def grads_close(got, truth64, ref32, like, rtol=1e-4):
-    """Per parameter tensor.  The gradients are ill-conditioned in fp32 (the std aggregator
-    divides rounding noise by sqrt(1e-5) wherever a message column is constant), so the
-    yardstick is the reference arithmetic's own fp32 noise: our error against an fp64
-    evaluation must stay within 4x the fp32 oracle's error against the same fp64 evaluation
-    (per tensor, or the worst relative noise over all tensors), plus rtol * max|grad|."""
-    o, rel_noise = 0, 0.0
+def grads_close(got, truth64, refs32, like, rtol=1e-4, factor=8):
+    """Per parameter tensor.  The early-layer gradients are ill-conditioned in fp32: the std
+    aggregator evaluates mean(x^2) - mean(x)^2, whose rounding error (~|x|^2 * 1e-7) is of the
+    order of 1e-5 + var wherever a message column is nearly constant over a segment, and
+    1/std multiplies the gradient.  Merely permuting the edge order changes the reference's
+    own fp32 gradients by ~1e-3 relative on the default init.  So the yardstick is the
+    reference arithmetic's fp32 noise measured in this test: our error against an fp64
+    evaluation must stay within `factor` x the fp32 oracle's error against the same fp64
+    evaluation (worst of the given fp32 evaluations, per tensor and network-wide relative),
+    plus rtol * max|grad|."""
+    o, rel_noise, noises = 0, 0.0, {}
     for k, v in like.items():
         n = v.numel()
-        t, r = truth64[o:o + n], ref32[o:o + n]
+        t = truth64[o:o + n]
+        noise = max(float(np.abs(r[o:o + n] - t).max()) for r in refs32)
         o += n
-        rel_noise = max(rel_noise, float(np.abs(r - t).max()) / max(float(np.abs(t).max()), 1e-30))
+        noises[k] = noise
+        rel_noise = max(rel_noise, noise / max(float(np.abs(t).max()), 1e-30))
     o = 0
     for k, v in like.items():
         n = v.numel()
-        g, t, r = got[o:o + n].astype(np.float64), truth64[o:o + n], ref32[o:o + n]
+        g, t = got[o:o + n].astype(np.float64), truth64[o:o + n]
         o += n
         scale = max(float(np.abs(t).max()), 1e-30)
-        noise = float(np.abs(r - t).max())
         err = float(np.abs(g - t).max())
-        assert err <= 4 * noise + (2 * rel_noise + rtol) * scale + 1e-9, (k, err, noise, scale, rel_noise)
+        assert err <= factor * noises[k] + (rel_noise + rtol) * scale + 1e-9, (k, err, noises[k], scale, rel_noise)
 
 
 @pytest.mark.parametrize('weights', ['init', 'trained'])
@@ -258,20 +265,22 @@ def test_gn_backward_vs_autograd(weights):
     torch.manual_seed(1)
     d_q = torch.randn(N)
     d_h = torch.randn(N, 64) * 0.1
+    perm = torch.randperm(ei.shape[1])
     flat, P, ea_i, h, q, st = run_forward(params, x, ei, ea, stash=True)
-    got_q = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV)).cpu().numpy()
-    grads_close(got_q, oracle_grads(params, x, ei, ea, d_q, None, torch.float64),
-                oracle_grads(params, x, ei, ea, d_q, None, torch.float32), params)
-    got_qh = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), d_h=d_h.to(DEV)).cpu().numpy()
-    grads_close(got_qh, oracle_grads(params, x, ei, ea, d_q, d_h, torch.float64),
-                oracle_grads(params, x, ei, ea, d_q, d_h, torch.float32), params)
-    got_h = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_h=d_h.to(DEV)).cpu().numpy()
-    grads_close(got_h, oracle_grads(params, x, ei, ea, d_q * 0, d_h, torch.float64),
-                oracle_grads(params, x, ei, ea, d_q * 0, d_h, torch.float32), params)
+
+    def check(got, dq, dh):
+        truth = oracle_grads(params, x, ei, ea, dq, dh, torch.float64)
+        refs = [oracle_grads(params, x, ei, ea, dq, dh, torch.float32),
+                oracle_grads(params, x, ei, ea, dq, dh, torch.float32, perm=perm)]
+        grads_close(got, truth, refs, params)
+    check(ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV)).cpu().numpy(), d_q, None)
+    check(ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), d_h=d_h.to(DEV)).cpu().numpy(), d_q, d_h)
+    check(ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_h=d_h.to(DEV)).cpu().numpy(), d_q * 0, d_h)
     # accumulate=True adds on top
-    g2 = torch.from_numpy(got_q).to(DEV).clone()
+    got_q = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV))
+    g2 = got_q.clone()
     ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), grad=g2, accumulate=True)
-    np.testing.assert_allclose(g2.cpu().numpy(), 2 * got_q, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(g2.cpu().numpy(), 2 * got_q.cpu().numpy(), rtol=1e-3, atol=1e-6)
 
 
 def test_learn_step_vs_reference_golden():
@@ -302,7 +311,7 @@ def test_learn_step_vs_reference_golden():
     assert abs(float(loss.item()) - float(d['loss'])) < 1e-5
     grad = ops().gn_backward(flat_b, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q)
     truth = oracle_grads(pb, x, ei, ea, d_q.cpu(), None, torch.float64)
-    grads_close(grad.cpu().numpy(), truth, d['grads'].astype(np.float64), pb)
+    grads_close(grad.cpu().numpy(), truth, [d['grads'].astype(np.float64)], pb)
     m = torch.zeros_like(flat_b)
     v = torch.zeros_like(flat_b)
     ops().adam_soft_update(flat_b, grad, m, v, flat_t, 1, lr=1e-3, tau=1e-3)
