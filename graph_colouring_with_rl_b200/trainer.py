@@ -172,3 +172,8 @@ def synthetic_transitions(adjs, frac_coloured, seed, device):
     host = dict(adj=env.adj.cpu(), cur_colour=cur.cpu(), next_colour=env.colour.cpu(), action=act.cpu(),
                 reward=env.reward.cpu(), done=env.done.cpu())
     return env.ns.copy(), host
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous split of n_items units (graphs) over `world` ranks -> [lo, hi) of `rank`."""
+    return n_items * rank // world, n_items * (rank + 1) // world
