@@ -170,7 +170,7 @@ def main():
     ap.add_argument('--graphs', type=int, default=4096)
     ap.add_argument('--vertices', type=int, default=200)
     ap.add_argument('--micro-graphs', type=int, default=512)
-    ap.add_argument('--math', default='fp32', choices=['fp32', 'tf32', '3xtf32'])
+    ap.add_argument('--math', default='fp32', choices=['fp32', 'bf16', 'bf16x3'])
     ap.add_argument('--rollout-graphs', type=int, default=10000)
     ap.add_argument('--rollout-vertices', type=int, default=50)
     ap.add_argument('--cpu-sample-graphs', type=int, default=8)

@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_PKG_DIR, 'libgcrl_b200.so')
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), 'include', 'gcrl_b200.h')
 
 GCRL_MATH_FP32 = 0
-GCRL_MATH_TF32 = 1
-GCRL_MATH_3XTF32 = 2
+GCRL_MATH_BF16 = 1
+GCRL_MATH_BF16X3 = 2
 
 _lib = None
 
@@ -32,6 +32,7 @@ SIGNATURES = {
     'gcrl_launch_count': (c_int64, []),
     'gcrl_prof_enable': (c_int, [c_int]),
     'gcrl_prof_read': (c_int, [P, P, c_int]),
+    'gcrl_selftest_tc': (c_int, [P, P, P, c_int64, c_int, P, P, P, c_int, P]),
     'gcrl_param_layout': (c_int, [c_int, c_int, c_int, P]),
     'gcrl_pack_workspace_bytes': (c_size_t, [c_int64, c_int64]),
     'gcrl_pack': (c_int, [P, c_int64, c_int64, P, P, P, P, P, P, c_size_t, P]),

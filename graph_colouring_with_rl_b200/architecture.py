@@ -25,7 +25,7 @@ from .principal_neighbourhood_aggregation import AGGREGATORS, SCALERS
 # device (LOCAL_RANK under torchrun), overridable with GCRL_DEVICE.
 DEVICE = os.environ.get('GCRL_DEVICE', 'cuda:%d' % int(os.environ.get('LOCAL_RANK', '0')))
 
-MATH_MODES = {'fp32': _lib.GCRL_MATH_FP32, 'tf32': _lib.GCRL_MATH_TF32, '3xtf32': _lib.GCRL_MATH_3XTF32}
+MATH_MODES = {'fp32': _lib.GCRL_MATH_FP32, 'bf16': _lib.GCRL_MATH_BF16, 'bf16x3': _lib.GCRL_MATH_BF16X3}
 
 
 def _device():

@@ -1,0 +1,210 @@
+// tc.cuh -- sm_100a tensor-core plumbing used by the edge kernels: mbarriers, TMA (bulk tensor
+// copies), TMEM allocation, tcgen05.mma (kind::f16, bf16 operands, fp32 accumulate in TMEM) with
+// shared-memory matrix descriptors, tcgen05.ld.  Inline PTX only; no CUTLASS.
+//
+// Precision scheme ("bf16x3"): every fp32 operand x is split into hi = bf16(x) and
+// lo = bf16(x - hi); a product A*B is issued as A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with fp32
+// accumulation, i.e. ~16 mantissa bits per operand (TF32 would give 10).  Mode "bf16" issues the
+// hi*hi term only.
+//
+// Operand tile format: a [R rows x 64] bf16 tile is R lines of 128 bytes; line r sits at byte
+// offset r*128 and its eight 16-byte chunks are XOR-swizzled with (r & 7) (SWIZZLE_128B).  For
+// 16-bit types this one byte layout is BOTH the canonical K-major operand (rows = M/N, columns =
+// K) and the canonical MN-major operand (rows = K, columns = M/N) of tcgen05 matrix descriptors,
+// so a tile written once serves the products that contract over features (message MLP, its
+// dgrads) and the ones that contract over edge rows (weight gradients).  (TF32 operands do not
+// have this property: MN-major tf32 requires the 32-byte-atom swizzle.)
+//
+// fp32 staging tiles (TMA landing, epilogue exchange, TMA store source) use "SW128 slabs":
+// [R x 64] fp32 as two slabs of [R x 32]; slab s holds columns [32s, 32s+32); row r of a slab is a
+// 128-byte line at r*128 with chunks XOR-swizzled by (r & 7) -- what a TMA box {32, R} with
+// CU_TENSOR_MAP_SWIZZLE_128B reads/writes; conflict-free both for row-per-lane and
+// column-per-lane access.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace gcrl {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// byte offset of 16-byte chunk c4 (0..15) of row r inside a tile whose slabs hold R rows
+template <int R>
+__device__ __forceinline__ uint32_t sw_off(int r, int c4) {
+    return (uint32_t)((c4 >> 3) * (R * 128) + r * 128 + ((((c4 & 7) ^ (r & 7))) << 4));
+}
+
+// ---- mbarrier ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("gcrl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// ---- fences ----------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMA -------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- TMEM ------------------------------------------------------------------------------------
+// one full warp; writes the base address (lane 0, column c) to *slot
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t base) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+
+// ---- tcgen05.mma -----------------------------------------------------------------------------
+// matrix descriptor of a SWIZZLE_128B operand starting at smem byte address `addr`:
+//   bits [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 2
+// K-major: SBO = 1024 (stride between 8-row groups), LBO unused (16).
+// MN-major: SBO = 1024 (stride between 8-K-row groups), LBO = stride between 64-element MN atoms
+// (unused here: every operand is exactly 64 wide).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::f16 with bf16 operands, fp32 accumulate
+//   [4,6) D fmt = 1 (f32) | [7,10) A fmt = 1 (bf16) | [10,13) B fmt = 1 | [15] A MN-major | [16] B MN-major
+//   [17,23) N >> 3 | [24,29) M >> 4
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
+// arrive on `bar` when all previously issued MMAs of this thread have completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// byte offset of 16-byte chunk cb (0..7, 8 bf16 each) of line r in a bf16 operand tile
+__device__ __forceinline__ uint32_t bf_off(int r, int cb) { return (uint32_t)(r * 128 + ((cb ^ (r & 7)) << 4)); }
+
+// split 8 consecutive floats into bf16 hi / lo chunks (16 bytes each)
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// D[R x 64] (+)= A[R x 64] * B[64 x 64]^T contracting over the 64 columns (K-major operands):
+// 4 K=16 steps; X3 adds the lo*hi and hi*lo correction terms.  a_lo/b_lo ignored when !X3.
+template <bool X3>
+__device__ __forceinline__ void issue_gemm_feat(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                uint32_t b_lo, uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t ah = make_desc(a_hi + 32 * k, 16, 1024), bh = make_desc(b_hi + 32 * k, 16, 1024);
+        umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
+        if (X3) {
+            umma_bf16(d_tmem, make_desc(a_lo + 32 * k, 16, 1024), bh, idesc, true);
+            umma_bf16(d_tmem, ah, make_desc(b_lo + 32 * k, 16, 1024), idesc, true);
+        }
+    }
+}
+// D[64 x 64] (+)= A[rows x 64]^T * B[rows x 64] contracting over `rows` edge rows (MN-major
+// operands, M = N = 64): rows/16 K=16 steps, each advancing two 8-row groups (2048 bytes).
+template <bool X3>
+__device__ __forceinline__ void issue_gemm_rows(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                uint32_t b_lo, uint32_t idesc, int rows, bool accumulate_first) {
+    for (int k = 0; k < rows / 16; ++k) {
+        const uint64_t ah = make_desc(a_hi + 2048 * k, 8192, 1024), bh = make_desc(b_hi + 2048 * k, 8192, 1024);
+        umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
+        if (X3) {
+            umma_bf16(d_tmem, make_desc(a_lo + 2048 * k, 8192, 1024), bh, idesc, true);
+            umma_bf16(d_tmem, ah, make_desc(b_lo + 2048 * k, 8192, 1024), idesc, true);
+        }
+    }
+}
+
+// ---- tcgen05.ld: 32 lanes x 32 consecutive 32-bit columns; thread i of the warp gets lane
+// (taddr.lane + i); the warp may only touch lanes [32*(warp%4), 32*(warp%4)+32) -------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+}  // namespace tc
+
+// host side: tensor map of a row-major fp32 matrix [rows, 64] with box {32, box_rows}, SWIZZLE_128B
+int make_tmap_rows64(CUtensorMap* out, const float* base, int64_t rows, int box_rows);
+
+}  // namespace gcrl

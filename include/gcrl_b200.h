@@ -47,8 +47,8 @@ typedef enum {
 
 /* math mode of the per-edge / per-vertex MLPs */
 #define GCRL_MATH_FP32 0     /* CUDA-core FFMA, fp32 operands and accumulate (parity mode) */
-#define GCRL_MATH_TF32 1     /* tcgen05 kind::tf32 tensor cores, fp32 accumulate in TMEM */
-#define GCRL_MATH_3XTF32 2   /* tcgen05 kind::tf32 with big/small operand split (near-fp32) */
+#define GCRL_MATH_BF16 1     /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM */
+#define GCRL_MATH_BF16X3 2   /* tcgen05, operands split hi+lo bf16, 3 MMAs per product (near-fp32) */
 
 const char* gcrl_last_error(void);
 int gcrl_version(void);
@@ -72,6 +72,12 @@ int gcrl_sm_count(void);
 int64_t gcrl_launch_count(void);
 int gcrl_prof_enable(int on);
 int gcrl_prof_read(double* ms, int64_t* launches, int n_kinds);
+
+/* Self-test of the tcgen05 / TMA / TMEM plumbing the edge kernels use (one CTA, bf16x3):
+ * D [128,64] = A[row0:row0+128] * W^T, DW [64,64] = A[rows]^T * A2[rows]; copy_out (may be NULL)
+ * receives a TMA store of the A tile.  A, A2, copy_out: [rows_total,64] fp32; W [64,64]. */
+int gcrl_selftest_tc(const float* A, const float* A2, const float* W, int64_t rows_total, int row0,
+                     float* D, float* DW, float* copy_out, int use_tma, void* stream);
 
 /* ---- parameter layout ------------------------------------------------------------------
  * One flat fp32 buffer in state_dict order (architecture.py:157-167): for block l=1..5
