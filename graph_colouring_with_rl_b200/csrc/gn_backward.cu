@@ -535,10 +535,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
     GCRL_CHECK_ARG(vdim >= 1 && vdim <= 64 && edim >= 1 && edim <= 64 && gdim >= 0 && gdim <= 64);
     GCRL_CHECK_ARG(N >= 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31));
     GCRL_CHECK_ARG(params && grad);
-    if (math_mode != GCRL_MATH_FP32) {
-        set_error("gcrl_gn_backward: math_mode %d not available in this build", math_mode);
-        return GCRL_ERR_INVALID;
-    }
+    GCRL_CHECK_ARG(math_mode == GCRL_MATH_FP32 || math_mode == GCRL_MATH_BF16 || math_mode == GCRL_MATH_BF16X3);
     cudaStream_t st = (cudaStream_t)stream;
     NetW net = make_net(params, vdim, edim, gdim);
     if (!accumulate) GCRL_CUDA(cudaMemsetAsync(grad, 0, (size_t)net.total * 4, st));

@@ -405,6 +405,23 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
     return GCRL_OK;
 }
 
+// gn_forward_tc.cu
+int launch_edge_fwd_tc(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
+                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
+
+// dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
+int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
+                         const float* e_prev, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
+                         int64_t N, int64_t E, float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax,
+                         cudaStream_t st) {
+    const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
+    if (math_mode != GCRL_MATH_FP32 && tc_ok)
+        return launch_edge_fwd_tc(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out,
+                                  agg, var, amin, amax, st);
+    return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
+}
+
 int launch_node_update(const NetW& net, int l /*0-based*/, bool with_extra, const float* agg, const float* h_in,
                        const int32_t* seg_off, const float* gfeat, const int32_t* vgraph, int64_t N,
                        float* h_out, float* Pi, float* Pj, float* q, float* u1_out, float* y1_out,
@@ -472,10 +489,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
     if (N == 0) return GCRL_OK;
     GCRL_CHECK_ARG(params && seg_off && x && q_out && (E == 0 || (src && dst && eattr)));
     GCRL_CHECK_ARG(gdim == 0 || (gfeat && vgraph));
-    if (math_mode != GCRL_MATH_FP32) {
-        set_error("gcrl_gn_forward: math_mode %d not available in this build", math_mode);
-        return GCRL_ERR_INVALID;
-    }
+    GCRL_CHECK_ARG(math_mode == GCRL_MATH_FP32 || math_mode == GCRL_MATH_BF16 || math_mode == GCRL_MATH_BF16X3);
     if (!ws || ws_bytes < gcrl_gn_forward_workspace_bytes(N, E, stash_p != nullptr)) {
         set_error("gcrl_gn_forward: workspace too small");
         return GCRL_ERR_WORKSPACE;
@@ -514,7 +528,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         float* e_out = last ? nullptr : (stash_p ? S.e[l] : eb[l & 1]);
         float* agg = stash_p ? S.agg[l] : aggb;
         float* hl = stash_p ? S.h[l] : hb[l & 1];
-        rc = launch_edge_fwd(net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
+        rc = launch_edge_fwd_mode(math_mode, net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
                              seg_off, src, dst, N, E, e_out, agg, stash_p ? S.var[l] : nullptr,
                              stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st);
         if (rc) return rc;
@@ -541,10 +555,7 @@ int gcrl_gn_block_forward(const float* params, int vdim, int edim, int gdim, int
     GCRL_CHECK_ARG(N >= 0 && E >= 0 && N < (1ll << 31) && E < (1ll << 31));
     if (N == 0) return GCRL_OK;
     GCRL_CHECK_ARG(params && seg_off && x && upd_out && (E == 0 || (src && dst && eattr && msg_out)));
-    if (math_mode != GCRL_MATH_FP32) {
-        set_error("gcrl_gn_block_forward: math_mode %d not available in this build", math_mode);
-        return GCRL_ERR_INVALID;
-    }
+    GCRL_CHECK_ARG(math_mode == GCRL_MATH_FP32 || math_mode == GCRL_MATH_BF16 || math_mode == GCRL_MATH_BF16X3);
     size_t need = 2 * align_up((size_t)N * 64 * 4) + align_up((size_t)N * 256 * 4) + align_up((size_t)N * 4) + 256;
     if (!ws || ws_bytes < need) {
         set_error("gcrl_gn_block_forward: workspace too small (need %zu)", need);
@@ -567,8 +578,8 @@ int gcrl_gn_block_forward(const float* params, int vdim, int edim, int gdim, int
         k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
         GCRL_LAUNCH_CHECK();
     }
-    rc = launch_edge_fwd(b, b.De != 64 || block == 1, Pi, Pj, eattr, seg_off, src, dst, N, E, msg_out, agg,
-                         nullptr, nullptr, nullptr, st);
+    rc = launch_edge_fwd_mode(math_mode, b, b.De != 64 || block == 1, Pi, Pj, eattr, seg_off, src, dst, N, E, msg_out,
+                              agg, nullptr, nullptr, nullptr, st);
     if (rc) return rc;
     // update MLP only (no next-block projections, no head)
     (void)qtmp;

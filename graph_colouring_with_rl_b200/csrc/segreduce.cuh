@@ -51,6 +51,14 @@ __device__ __forceinline__ void stat_final(const Stat& s, int32_t deg, float& me
     mn = s.mn; mx = s.mx;
 }
 
+// value-only variant (inference: nobody reads the arg slots)
+__device__ __forceinline__ void stat_add_noarg(Stat& s, float v) {
+    s.sum += v;
+    s.sq = fmaf(v, v, s.sq);
+    s.mn = fminf(s.mn, v);
+    s.mx = fmaxf(s.mx, v);
+}
+
 struct AggOut {
     float* agg;       // [N,256] mean|min|max|std
     float* var;       // [N,64] raw variance (relu' mask for backward) or null
@@ -83,10 +91,11 @@ struct Carry {
     int32_t dst;  // -1 = empty
 };
 
-// Phase A: all 256 threads.  M_s: tile [128][ld] in smem, dst_s[128] destination ids of rows.
-__device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const int32_t* dst_s,
-                                                 int nrows, int32_t slot0, RedScratch* sc,
-                                                 const AggOut& out) {
+// Phase A: all 256 threads.  load(r, col) reads element (r, col) of the 128-row message tile in
+// shared memory, dst_s[128] destination ids of rows.
+template <class LoadFn>
+__device__ __forceinline__ void tile_reduce_scan_fn(LoadFn load, const int32_t* dst_s, int nrows,
+                                                    int32_t slot0, RedScratch* sc, const AggOut& out) {
     const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
     const int r0 = q * 32;
     const int r1 = min(r0 + 32, nrows);
@@ -110,7 +119,7 @@ __device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const
             stat_init(cur);
             cd = d;
         }
-        stat_add(cur, M_s[r * ld + col], slot0 + r);
+        stat_add(cur, load(r, col), slot0 + r);
     }
     const int w = seen ? 1 : 0;
     sc->f[w][0][q][col] = cur.sum; sc->f[w][1][q][col] = cur.sq;
@@ -120,6 +129,70 @@ __device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const
         sc->head_dst[q] = hd;
         sc->tail_dst[q] = seen ? cd : -1;
     }
+}
+
+// Phase A for the SW128-slab fp32 tile of the tensor-core kernels (tc.cuh): rows are walked in
+// groups of 8 so the XOR swizzle (chunk ^ (r & 7)) folds into eight per-thread constant offsets;
+// the 8 values of a group are loaded up front and segment boundaries come from a per-tile bit
+// mask (bit r set = row r starts a new destination), so no load sits on the branch chain.
+template <bool WANT_ARG>
+__device__ __forceinline__ void tile_reduce_scan_sw(const float* L, const int32_t* dst_s, const uint32_t* start_bits,
+                                                    int nrows, int32_t slot0, RedScratch* sc, const AggOut& out) {
+    const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int r0 = q * 32;
+    const int r1 = min(r0 + 32, nrows);
+    if (r0 >= r1) return;
+    const int c4 = col >> 2, cc = c4 & 7;
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(L) + (c4 >> 3) * (128 * 128) + (col & 3) * 4;
+    const uint32_t starts = start_bits[q] & ~1u;    // a boundary at the quarter's first row is the head itself
+    Stat cur;
+    stat_init(cur);
+    int32_t cd = dst_s[r0];
+    const int32_t hd = cd;
+    bool seen = false;
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+        const int rb = r0 + 8 * g;
+        if (rb >= r1) break;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float*>(base + (rb + k) * 128 + ((cc ^ k) << 4));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = rb + k;
+            if (r < r1) {
+                if ((starts >> (8 * g + k)) & 1u) {
+                    if (!seen) {
+                        sc->f[0][0][q][col] = cur.sum; sc->f[0][1][q][col] = cur.sq;
+                        sc->f[0][2][q][col] = cur.mn;  sc->f[0][3][q][col] = cur.mx;
+                        sc->a[0][0][q][col] = cur.amn; sc->a[0][1][q][col] = cur.amx;
+                        seen = true;
+                    } else {
+                        agg_write(out, cd, col, cur);
+                    }
+                    stat_init(cur);
+                    cd = dst_s[r];
+                }
+                if (WANT_ARG) stat_add(cur, v[k], slot0 + r);
+                else stat_add_noarg(cur, v[k]);
+            }
+        }
+    }
+    const int w = seen ? 1 : 0;
+    sc->f[w][0][q][col] = cur.sum; sc->f[w][1][q][col] = cur.sq;
+    sc->f[w][2][q][col] = cur.mn;  sc->f[w][3][q][col] = cur.mx;
+    sc->a[w][0][q][col] = cur.amn; sc->a[w][1][q][col] = cur.amx;
+    if (col == 0) {
+        sc->head_dst[q] = hd;
+        sc->tail_dst[q] = seen ? cd : -1;
+    }
+}
+
+// M_s: tile [128][ld] row-major in smem
+__device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const int32_t* dst_s,
+                                                 int nrows, int32_t slot0, RedScratch* sc,
+                                                 const AggOut& out) {
+    tile_reduce_scan_fn([=](int r, int col) { return M_s[r * ld + col]; }, dst_s, nrows, slot0, sc, out);
 }
 
 // Phase B: threads 0..63 only (after a __syncthreads following phase A).

@@ -141,19 +141,34 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // byte offset of 16-byte chunk cb (0..7, 8 bf16 each) of line r in a bf16 operand tile
 __device__ __forceinline__ uint32_t bf_off(int r, int cb) { return (uint32_t)(r * 128 + ((cb ^ (r & 7)) << 4)); }
 
+// two floats -> packed bf16x2 (round to nearest even); `lo` operand lands in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// split (x0, x1) into packed hi = bf16(x) and lo = bf16(x - hi)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
 // split 8 consecutive floats into bf16 hi / lo chunks (16 bytes each)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    split2(x[0], x[1], hi.x, lo.x);
+    split2(x[2], x[3], hi.y, lo.y);
+    split2(x[4], x[5], hi.z, lo.z);
+    split2(x[6], x[7], hi.w, lo.w);
+}
+template <bool X3>
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+    if (X3) {
+        split2(v.x, v.y, hi.x, lo.x);
+        split2(v.z, v.w, hi.y, lo.y);
+    } else {
+        hi.x = pack_bf16x2(v.x, v.y);
+        hi.y = pack_bf16x2(v.z, v.w);
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // D[R x 64] (+)= A[R x 64] * B[64 x 64]^T contracting over the 64 columns (K-major operands):
@@ -200,6 +215,58 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
           "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// pointer to 16-byte chunk c4 of row r of a 128-row fp32 SW128-slab tile
+__device__ __forceinline__ float* l_ptr(float* L, int r, int c4) {
+    return reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(L) + sw_off<128>(r, c4));
+}
+__device__ __forceinline__ const float* l_ptr(const float* L, int r, int c4) {
+    return reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(L) + sw_off<128>(r, c4));
+}
+
+// weights [64 x ld] row-major (columns col0..col0+63) -> bf16 hi/lo operand tiles (rows = out, cols = in)
+__device__ __forceinline__ void load_weight_tile(const float* W, int ld, int col0, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                 int tid, int nthreads) {
+    for (int t = tid; t < 64 * 8; t += nthreads) {
+        const int o = t >> 3, cb = t & 7;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = W[o * ld + col0 + 8 * cb + j];
+        uint4 h, l;
+        split8(x, h, l);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(hi) + bf_off(o, cb)) = h;
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(lo) + bf_off(o, cb)) = l;
+    }
+}
+
+// 8 floats -> bf16 chunk(s) of an operand tile at (row, chunk cb)
+template <bool X3>
+__device__ __forceinline__ void store_split8(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int row, int cb) {
+    uint4 h, l;
+    if (X3) {
+        split8(x, h, l);
+    } else {
+        h = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(hi) + bf_off(row, cb)) = h;
+    if (X3) *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(lo) + bf_off(row, cb)) = l;
+}
+
+// fp32 SW128-slab tile (128 rows) -> bf16 hi/lo operand tile; half a warp per 256-byte row
+template <bool X3>
+__device__ __forceinline__ void convert_tile128(const float* L, __nv_bfloat16* hi, __nv_bfloat16* lo, int tid) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int t = it * 256 + tid;
+        const int r = t >> 4, c4 = t & 15;
+        const float4 v = *reinterpret_cast<const float4*>(l_ptr(L, r, c4));
+        uint2 h, l;
+        split4<X3>(v, h, l);
+        const uint32_t off = bf_off(r, c4 >> 1) + (c4 & 1) * 8;
+        *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(hi) + off) = h;
+        if (X3) *reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(lo) + off) = l;
+    }
 }
 
 }  // namespace tc

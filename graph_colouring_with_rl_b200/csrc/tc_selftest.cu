@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
                                                        float* __restrict__ D, float* __restrict__ DW, int use_tma,
                                                        int do_store) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    SelfSmem& S = *reinterpret_cast<SelfSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    SelfSmem& S = *reinterpret_cast<SelfSmem*>(smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         tc::mbar_init(&S.bar_tma, 1);

