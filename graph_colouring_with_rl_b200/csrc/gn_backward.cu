@@ -511,6 +511,15 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
     return GCRL_OK;
 }
 
+// gn_backward_tc.cu
+int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
+                        float* ca, float* cb, cudaStream_t st);
+int launch_edge_bwd_tc(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
+                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
+                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
+                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
+
 }  // namespace gcrl
 
 using namespace gcrl;
@@ -522,7 +531,7 @@ extern "C" {
 size_t gcrl_gn_backward_workspace_bytes(int64_t N, int64_t E) {
     const size_t n64 = align_up((size_t)N * 64 * 4);
     size_t b = 2 * align_up((size_t)E * 64 * 4);   // d e ping-pong
-    b += 6 * n64;                                   // dh x2, du1, dPi, dPj, gather scratch
+    b += 8 * n64;                                   // dh x2, du1, dPi, dPj, gather scratch, PNA coefficients x2
     b += align_up((size_t)N * 256 * 4);             // d agg
     return b + 256;
 }
@@ -555,6 +564,8 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
     float* dPi = ar.take<float>((size_t)N * 64);
     float* dPj = ar.take<float>((size_t)N * 64);
     float* scratch = ar.take<float>((size_t)N * 64);
+    float* coef_a = ar.take<float>((size_t)N * 64);
+    float* coef_b = ar.take<float>((size_t)N * 64);
     float* dagg = ar.take<float>((size_t)N * 256);
     // gradient views, laid out like params
     auto G = [&](const float* p) { return grad + (p - params); };
@@ -615,7 +626,14 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)N * 64 * 4, st));
         GCRL_CUDA(cudaMemsetAsync(dPj, 0, (size_t)N * 64 * 4, st));
         float* de_prev = (l > 0) ? deb[l & 1] : nullptr;
-        if (E > 0) {
+        const bool tc_ok = (l == 0) ? (b.De <= 8) : (b.De == 64);
+        if (E > 0 && math_mode != GCRL_MATH_FP32 && tc_ok) {
+            RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, st));
+            RC(launch_edge_bwd_tc(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
+                                  b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E,
+                                  (l == GCRL_N_BLOCKS - 1) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
+                                  S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
+        } else if (E > 0) {
             EdgeBwdArgs a;
             a.Pi = S.Pi[l]; a.Pj = S.Pj[l];
             a.e_prev = (l == 0) ? eattr : S.e[l - 1]; a.De = b.De;

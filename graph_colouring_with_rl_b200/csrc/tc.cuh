@@ -186,6 +186,21 @@ __device__ __forceinline__ void issue_gemm_feat(uint32_t d_tmem, uint32_t a_hi, 
         }
     }
 }
+// D[R x 64] (+)= A[R x 64] * W[64 x 64] (no transpose): A K-major, W read as an MN-major operand
+// (rows of the weight tile = contraction index): the B descriptor walks 16 rows (2048 bytes) per step.
+template <bool X3>
+__device__ __forceinline__ void issue_gemm_featT(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                 uint32_t b_lo, uint32_t idesc, bool accumulate_first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t ah = make_desc(a_hi + 32 * k, 16, 1024), bh = make_desc(b_hi + 2048 * k, 8192, 1024);
+        umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
+        if (X3) {
+            umma_bf16(d_tmem, make_desc(a_lo + 32 * k, 16, 1024), bh, idesc, true);
+            umma_bf16(d_tmem, ah, make_desc(b_lo + 2048 * k, 8192, 1024), idesc, true);
+        }
+    }
+}
 // D[64 x 64] (+)= A[rows x 64]^T * B[rows x 64] contracting over `rows` edge rows (MN-major
 // operands, M = N = 64): rows/16 K=16 steps, each advancing two 8-row groups (2048 bytes).
 template <bool X3>
