@@ -170,7 +170,8 @@ def main():
     ap.add_argument('--graphs', type=int, default=4096)
     ap.add_argument('--vertices', type=int, default=200)
     ap.add_argument('--micro-graphs', type=int, default=512)
-    ap.add_argument('--math', default='fp32', choices=['fp32', 'bf16', 'bf16x3'])
+    ap.add_argument('--math', default='bf16x3', choices=['fp32', 'bf16', 'bf16x3'],
+                    help='fp32: CUDA-core FFMA parity path; bf16x3: tcgen05 with hi/lo split operands (near-fp32); bf16: tcgen05')
     ap.add_argument('--rollout-graphs', type=int, default=10000)
     ap.add_argument('--rollout-vertices', type=int, default=50)
     ap.add_argument('--cpu-sample-graphs', type=int, default=8)
@@ -280,7 +281,9 @@ def main():
             if k in bytes_per_edge:
                 kernels[k]['gbps'] = bytes_per_edge[k] * E_micro / (avg * 1e-3) / 1e9
     dom = max((k for k in kernels if k in bytes_per_edge), key=lambda k: kernels[k]['share_of_step'])
-    roofline = {'bound': 'hbm', 'kernel': 'k_edge_%s' % dom, 'achieved': kernels[dom]['gbps'], 'peak': hbm_peak,
+    kname = {'edge_fwd_first': 'k_edge_fwd%s<first>', 'edge_fwd': 'k_edge_fwd%s', 'edge_fwd_last': 'k_edge_fwd%s<last>',
+             'edge_bwd_first': 'k_edge_bwd%s<first>', 'edge_bwd': 'k_edge_bwd%s', 'edge_bwd_last': 'k_edge_bwd%s<last>'}[dom] % ('' if args.math == 'fp32' else '_tc')
+    roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': kernels[dom]['gbps'], 'peak': hbm_peak,
                 'unit': 'GB/s', 'frac': kernels[dom]['gbps'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': bytes_per_edge[dom] * E_micro,
                 'share_of_step': kernels[dom]['share_of_step']}
@@ -288,7 +291,7 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32' if args.math == 'fp32' else args.math, 'data': 'synthetic',
+        'dtype': {'fp32': 'f32', 'bf16x3': 'bf16x3 (hi+lo split operands, f32 accumulate)', 'bf16': 'bf16 (f32 accumulate)'}[args.math], 'data': 'synthetic',
         'config': {'workload': 'replay minibatch %d graphs x %d vertices fwd+bwd per GPU, ER(0.5), states 50%% coloured '
                                '(BASELINE.json configs[4])' % (G, n),
                    'global_graphs': G * world, 'edges_per_gpu': int(batch.n_edges), 'micro_batch_graphs': args.micro_graphs,
