@@ -240,6 +240,7 @@ def main():
         barrier()
         return max_over_ranks(a.elapsed_time(b)) / steps
 
+    log('[bench] rank %d: agent + batch ready' % rank)
     # ---- headline: resident inputs ------------------------------------------------------------------
     step_resident = lambda: learner.fwd_bwd(batch, q_next)
     for _ in range(args.warmup):
@@ -256,6 +257,7 @@ def main():
     lib.gcrl_prof_read(ms_k, cnt_k, 8)
     lib.gcrl_prof_enable(0)
     value = G * world / (ms_step * 1e-3)
+    log('[bench] rank %d: resident %.1f ms/step' % (rank, ms_step))
 
     # ---- e2e: host buffers -> public API -> loss on the host -------------------------------------------
     def step_e2e():
@@ -266,6 +268,7 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     clk = clocks.stop()
     e2e_value = G * world / (ms_e2e * 1e-3)
+    log('[bench] rank %d: e2e %.1f ms/step' % (rank, ms_e2e))
     h2d = TransitionBatch.host_bytes(host)
 
     # ---- roofline of the dominant kernel (edge backward, blocks 2-4) -------------------------------------
