@@ -513,12 +513,22 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
 
 // gn_backward_tc.cu
 int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
-                        float* ca, float* cb, cudaStream_t st);
+                        float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
+                        float* gb2_vertex, cudaStream_t st);
 int launch_edge_bwd_tc(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
+// gn_backward_ws.cu (warp-specialised pipeline; default)
+int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
+                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
+                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
+                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
+// GCRL_EDGE_IMPL=tc selects the older single-group tensor-core kernels (A/B comparisons)
+bool use_ws_kernels();
+
 
 }  // namespace gcrl
 
@@ -628,8 +638,15 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         float* de_prev = (l > 0) ? deb[l & 1] : nullptr;
         const bool tc_ok = (l == 0) ? (b.De <= 8) : (b.De == 64);
         if (E > 0 && math_mode != GCRL_MATH_FP32 && tc_ok) {
-            RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, st));
-            RC(launch_edge_bwd_tc(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
+            // the pipelined kernel takes the arg-min/max terms pre-added to d e_l (a workspace buffer
+            // nobody else reads); block 5 has no d e_l and applies them itself
+            // block 5 (e_5 recomputed in-kernel: a longer per-tile chain) is still faster on the single-group kernel
+            const bool ws = use_ws_kernels() && de_cur != nullptr;
+            float* de_scatter = ws ? const_cast<float*>(de_cur) : nullptr;
+            float* gb2_vertex = nullptr;     // (only the pipelined kernel's block-5 variant takes db2 from here)
+            RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
+                                   gb2_vertex, st));
+            RC((ws ? launch_edge_bwd_ws : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E,
                                   (l == GCRL_N_BLOCKS - 1) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
                                   S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));

@@ -30,9 +30,17 @@ namespace gcrl {
 using namespace tc;
 
 // ca = g_mean/deg - [var>0] g_std * mean / (deg * std),  cb = [var>0] g_std / (deg * std)
+// With de_scatter != null the min / max gradient terms are added to d e_l here (two scattered reds per
+// (vertex, column): 1/(n-1) of the elements) so that the edge kernel's dm pass is purely dense:
+//   d e_l[argmin[v,c], c] += g_min[v,c],  d e_l[argmax[v,c], c] += g_max[v,c].
 __global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __restrict__ agg,
                                const float* __restrict__ var, const int32_t* __restrict__ seg_off, int64_t N,
-                               float* __restrict__ ca, float* __restrict__ cb) {
+                               float* __restrict__ ca, float* __restrict__ cb, const int32_t* __restrict__ amin,
+                               const int32_t* __restrict__ amax, float* __restrict__ de_scatter,
+                               float* __restrict__ gb2_vertex) {
+    // gb2_vertex != null (block 5, pipelined kernel): db2 = sum over edges of dm = sum_v (g_mean + g_min + g_max)
+    // (the std term sums to zero over a segment), accumulated here instead of in the edge kernel
+    float bacc = 0.f;
     const int64_t total = N * 64;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = t >> 6;
@@ -48,6 +56,18 @@ __global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __re
         }
         ca[t] = a;
         cb[t] = b;
+        if (gb2_vertex && deg > 0.f) bacc += dagg[v * 256 + c] + dagg[v * 256 + 64 + c] + dagg[v * 256 + 128 + c];
+        if (de_scatter && deg > 0.f) {
+            atomicAdd(de_scatter + (int64_t)amin[t] * 64 + c, dagg[v * 256 + 64 + c]);
+            atomicAdd(de_scatter + (int64_t)amax[t] * 64 + c, dagg[v * 256 + 128 + c]);
+        }
+    }
+    if (gb2_vertex) {       // blockDim = 256 and a grid stride that is a multiple of 64: a thread's column is fixed
+        __shared__ float red[256];
+        red[threadIdx.x] = bacc;
+        __syncthreads();
+        if (threadIdx.x < 64)
+            atomicAdd(&gb2_vertex[threadIdx.x], red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192]);
     }
 }
 
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_bwd_tc(const __grid_constant__ 
         }
         fence_proxy_async();
         __syncthreads();                                                                   // #2
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
             tc_fence_after();
             if (!FIRST) {
                 issue_gemm_feat<X3>(t_acc1, smem_u32(S.B1[0]), smem_u32(S.B1[1]), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), id_feat, false);
@@ -281,7 +301,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_bwd_tc(const __grid_constant__ 
         tc_fence_before();
         __syncthreads();                                                                   // #3
         if (LAST) {
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
                 tc_fence_after();
                 issue_gemm_feat<X3>(t_acc2, smem_u32(S.B2[0]), smem_u32(S.B2[1]), smem_u32(S.W2[0]), smem_u32(S.W2[1]), id_feat, false);
                 umma_commit(&S.bar_mma);
@@ -347,7 +367,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_bwd_tc(const __grid_constant__ 
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();                                                                   // #4
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
             tc_fence_after();
             // G3: dW2 += dm^T hid ; G4: d hid = dm W2
             issue_gemm_rows<X3>(t_w2, smem_u32(S.B3[0]), smem_u32(S.B3[1]), smem_u32(S.B2[0]), smem_u32(S.B2[1]), id_rows, 128, !first_tile);
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_bwd_tc(const __grid_constant__ 
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();                                                                   // #5
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
             tc_fence_after();
             // G5: dC += dz1^T e_{l-1} ; G6: d e_{l-1} = dz1 C ; G7: per-segment sums of dz1
             issue_gemm_rows<X3>(t_c, smem_u32(S.B3[0]), smem_u32(S.B3[1]), smem_u32(S.B1[0]), smem_u32(S.B1[1]), id_rows, 128, !first_tile);
@@ -501,12 +521,13 @@ static int launch_bwd_variant(const CUtensorMap& te, const CUtensorMap& tm, cons
 }
 
 int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
-                        float* ca, float* cb, cudaStream_t st) {
+                        float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
+                        float* gb2_vertex, cudaStream_t st) {
     if (N == 0) return GCRL_OK;
     int64_t blocks = (N * 64 + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_pna_bwd_coef<<<(int)blocks, 256, 0, st>>>(dagg, agg, var, seg_off, N, ca, cb);
+    k_pna_bwd_coef<<<(int)blocks, 256, 0, st>>>(dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

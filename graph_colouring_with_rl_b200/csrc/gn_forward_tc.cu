@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256, 2) k_edge_fwd_tc(const __grid_constant__ 
                 }
                 fence_proxy_async();
                 __syncthreads();
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
                     // ---- 3. G1 -------------------------------------------------------------------------------
                     tc_fence_after();
                     issue_gemm_feat<X3>(t_acc1, smem_u32(S.B[0]), smem_u32(S.B[1]), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, false);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256, 2) k_edge_fwd_tc(const __grid_constant__ 
             fence_proxy_async();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {   // one elected lane of a converged warp: no per-thread election loop around each UMMA
                 // ---- 6. G2 -------------------------------------------------------------------------------
                 tc_fence_after();
                 issue_gemm_feat<X3>(t_acc2, smem_u32(S.B[0]), smem_u32(S.B[1]), smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);

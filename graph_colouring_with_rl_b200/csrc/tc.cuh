@@ -52,7 +52,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, don't spin
+    return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is open)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
@@ -82,9 +92,35 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(smem_u32(smem_dst)), "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// L2 eviction policies for the streamed edge tensors: they are touched once per launch and must not push the
+// per-vertex arrays (Pi, Pj, dPi, dPj, coefficients: re-used by every tile of a graph) out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(m), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, int c0, int c1, const void* smem_src, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int c0, int c1, const void* smem_src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+// contiguous global range -> L2 (no shared-memory destination): lets a kernel keep more bytes in
+// flight than its landing buffers hold; addr 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -100,6 +136,18 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
 template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t base) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+
+// one lane of a converged warp (elect.sync): code under `if (elect_one())` is single-threaded and the
+// compiler knows it, so tcgen05.mma / commit are emitted once instead of inside a per-thread election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // ---- tcgen05.mma -----------------------------------------------------------------------------
