@@ -252,7 +252,9 @@ def main():
     lib.gcrl_prof_read(ms_k, cnt_k, 8)            # drop warm-up records
     launches0 = lib.gcrl_launch_count()
     clocks = ClockSampler(local_rank)
+    torch.cuda.profiler.start()                   # `ncu --profile-from-start off` sees exactly the timed steps
     ms_step = timed(step_resident, args.steps)
+    torch.cuda.profiler.stop()
     launches = lib.gcrl_launch_count() - launches0
     lib.gcrl_prof_read(ms_k, cnt_k, 8)
     lib.gcrl_prof_enable(0)

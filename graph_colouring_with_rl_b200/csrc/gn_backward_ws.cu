@@ -52,8 +52,8 @@ struct BwdWsSmem {
     float b2[64];
     float bsum[64];
     uint64_t bar_Efull[WS_NE], bar_Eempty[WS_NE], bar_MDfull[WS_NMD], bar_MDempty[WS_NMD];
-    uint64_t bar_B1full[2], bar_B1free[2], bar_accAfree[2], bar_accBfree[2];
-    uint64_t bar_acc1full[2], bar_acc2full[2], bar_acc4full[2], bar_acc6full[2];
+    uint64_t bar_B1full[2], bar_B1free[2], bar_accBfree[2], bar_acc2full[2], bar_acc6full[2];
+    uint64_t bar_accAfree[3], bar_acc1full[3], bar_acc4full[3];      // ACC_A (and the relu mask) is triple-buffered
     uint64_t bar_B2full, bar_B3full, bar_dz1full, bar_B2read, bar_done;
     uint64_t bar_OUTfull[2];
     uint32_t tmem_base;
@@ -160,14 +160,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(&S.bar_B1full[i], 4);
             mbar_init(&S.bar_B1free[i], 1);
-            mbar_init(&S.bar_accAfree[i], 12);
             mbar_init(&S.bar_accBfree[i], 4);
-            mbar_init(&S.bar_acc1full[i], 1);
             mbar_init(&S.bar_acc2full[i], 1);
-            mbar_init(&S.bar_acc4full[i], 1);
             mbar_init(&S.bar_acc6full[i], 1);
             mbar_init(&S.bar_OUTfull[i], 4);
         }
+        for (int i = 0; i < 3; ++i) { mbar_init(&S.bar_accAfree[i], 12); mbar_init(&S.bar_acc1full[i], 1); mbar_init(&S.bar_acc4full[i], 1); }
         mbar_init(&S.bar_B2full, 8);
         mbar_init(&S.bar_B3full, 4);
         mbar_init(&S.bar_dz1full, 8);
@@ -190,7 +188,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-    const uint32_t t_accA0 = tmem, t_accB0 = tmem + 128, t_w2 = tmem + 256, t_c = tmem + 320, t_hm = tmem + 384;
+    const uint32_t t_accA0 = tmem, t_accB0 = tmem + 192, t_w2 = tmem + 320, t_c = tmem + 384, t_hm = tmem + 448;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
 
     const int64_t n_tiles = ((int64_t)a.E + TILE - 1) / TILE;
@@ -298,8 +296,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 if (!FIRST) {
                     const uint32_t b1_hi = smem_u32(S.B1[s]);
                     if (elect_one()) {
-                        issue_gemm_feat<X3>(t_accA0 + 64 * s, b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
-                        umma_commit(&S.bar_acc1full[s]);
+                        issue_gemm_feat<X3>(t_accA0 + 64 * (j % 3), b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
+                        umma_commit(&S.bar_acc1full[j % 3]);
                     }
                     __syncwarp();
                 }
@@ -323,8 +321,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 WS_TR(lane == 0, 1, i, 1);
                 if (elect_one()) {
                     issue_gemm_rows<X3>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
-                    issue_gemm_featT<X3>(t_accA0 + 64 * s, b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);
-                    umma_commit(&S.bar_acc4full[s]);
+                    issue_gemm_featT<X3>(t_accA0 + 64 * (i % 3), b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);
+                    umma_commit(&S.bar_acc4full[i % 3]);
                 }
                 __syncwarp();
                 WS_TR(lane == 0, 1, i, 2);
@@ -381,7 +379,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
 #pragma unroll
             for (int t = 0; t < 4; ++t) { d4[t] = nd[t]; s4[t] = ns[t]; }
             load_ids(i + 1);
-            mbar_wait(&S.bar_accAfree[s], ph ^ 1);
+            mbar_wait(&S.bar_accAfree[i % 3], ((i / 3) & 1) ^ 1);
             tc_fence_after();
             WS_TR(wtid == 0, 3, i, 0);
 #pragma unroll
@@ -435,7 +433,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
 #pragma unroll
                     for (int c = 0; c < 32; ++c) v[c] += ca_[c];
                 }
-                tmem_st_16x256b_x8(t_accA0 + 64 * s + ((uint32_t)(32 * q + 16 * g) << 16), v);
+                tmem_st_16x256b_x8(t_accA0 + 64 * (i % 3) + ((uint32_t)(32 * q + 16 * g) << 16), v);
             }
             tmem_st_wait();
             mbar_wait(&S.bar_B1free[s], ph ^ 1);        // the staging use of B1[s] two tiles ago has been stored
@@ -522,7 +520,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     const int R = 32 * (t >> 2) + (wtid >> 4) + 8 * (t & 3);
                     dv[t] = R < nrows ? __ldg(a.dst + t0 + R) : -1;
                 }
-                if (i > 0) mbar_wait(&S.bar_acc4full[s ^ 1], ((i - 1) >> 1) & 1);    // G3/G4 of the previous tile read B3
+                if (i > 0) mbar_wait(&S.bar_acc4full[(i - 1) % 3], ((i - 1) / 3) & 1);    // G3/G4 of the previous tile read B3
                 WS_TR(wtid == 0, 4, i, 0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -586,7 +584,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 const int32_t slot_e = t0 + row;
                 if (i > 0) epilogue4(i - 1);
                 mbar_wait(&S.bar_acc2full[s], ph);
-                if (i > 0) mbar_wait(&S.bar_acc4full[s ^ 1], ((i - 1) >> 1) & 1);
+                if (i > 0) mbar_wait(&S.bar_acc4full[(i - 1) % 3], ((i - 1) / 3) & 1);
                 tc_fence_after();
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
@@ -641,11 +639,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
         __nv_bfloat16* b2l = reinterpret_cast<__nv_bfloat16*>(S.B2 + 16384);
         for (int i = 0; i < n_cta; ++i) {
             const int s = i & 1, ph = (i >> 1) & 1;
-            const uint32_t t_acc = t_accA0 + 64 * s + lane_addr + 32 * half;
+            const int a3 = i % 3, pa = (i / 3) & 1;
+            const uint32_t t_acc = t_accA0 + 64 * a3 + lane_addr + 32 * half;
             uint32_t hm = 0u;
             // ---- epilogue 1: hid = relu(acc1) ---------------------------------------------------------------------
             if (FIRST) mbar_wait(&S.bar_B1full[s], ph);
-            else mbar_wait(&S.bar_acc1full[s], ph);
+            else mbar_wait(&S.bar_acc1full[a3], pa);
             tc_fence_after();
             WS_TR(tr, 5, i, 0);
             {
@@ -664,14 +663,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     store_split8<X3>(x, b2h, b2l, row, 4 * half + c);
                 }
             }
-            tmem_st_x1(t_hm + 2 * s + half + lane_addr, hm);      // relu mask of this row / column half, for WG_D
+            tmem_st_x1(t_hm + 2 * a3 + half + lane_addr, hm);      // relu mask of this row / column half, for WG_D
             tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
             WS_TR(tr, 5, i, 2);
             warp_arrive(&S.bar_B2full, lane);
             // ---- epilogue 3: dz1 = d hid * relu' -> B2 (G3/G4 have finished with hid) -----------------------------------
-            mbar_wait(&S.bar_acc4full[s], ph);
+            mbar_wait(&S.bar_acc4full[a3], pa);
             tc_fence_after();
             WS_TR(tr, 5, i, 3);
             {
@@ -689,7 +688,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             tc_fence_before();
             WS_TR(tr, 5, i, 4);
             warp_arrive(&S.bar_dz1full, lane);
-            warp_arrive(&S.bar_accAfree[s], lane);
+            warp_arrive(&S.bar_accAfree[a3], lane);
         }
         // ---- weight gradients: TMEM -> global (one atomic pass per CTA) ----------------------------------------------------
         mbar_wait(&S.bar_done, 0);
@@ -735,12 +734,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     const int32_t d0 = __shfl_sync(0xffffffffu, my_dst, 0);
                     const int bpos = nb ? (__ffs(sbits) - 1) : 0;
                     const int32_t d1 = __shfl_sync(0xffffffffu, my_dst, bpos);
-                    const uint32_t t_acc = t_accA0 + 64 * s + lane_addr;
-                    mbar_wait(&S.bar_acc4full[s], ph);
+                    const int a3 = i % 3;
+                    const uint32_t t_acc = t_accA0 + 64 * a3 + lane_addr;
+                    mbar_wait(&S.bar_acc4full[a3], (i / 3) & 1);
                     tc_fence_after();
                     WS_TR(wtid == 0, 6, i, 3);
                     uint32_t hm0, hm1;
-                    tmem_ld_x2(t_hm + 2 * s + lane_addr, hm0, hm1);
+                    tmem_ld_x2(t_hm + 2 * a3 + lane_addr, hm0, hm1);
 #pragma unroll 1
                     for (int hf = 0; hf < 2; ++hf) {
                         const uint32_t hm = hf ? hm1 : hm0;
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     }
                     tc_fence_before();
                     WS_TR(wtid == 0, 6, i, 4);
-                    warp_arrive(&S.bar_accAfree[s], lane);
+                    warp_arrive(&S.bar_accAfree[a3], lane);
                 }
             }
         }
@@ -857,7 +857,7 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
     a.m = m; a.de = de; a.trace = nullptr;
     {
         static int pf = -1;
-        if (pf < 0) { const char* e = getenv("GCRL_WS_PF"); pf = e ? atoi(e) : 2; }
+        if (pf < 0) { const char* e = getenv("GCRL_WS_PF"); pf = e ? atoi(e) : 0; }
         a.pf = pf;
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; }
