@@ -410,6 +410,13 @@ int launch_edge_fwd_tc(const BlockW& b, bool first, bool x3, const float* Pi, co
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
                        float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
 
+// gn_forward_ws.cu (warp-specialised pipeline; default, GCRL_EDGE_IMPL=tc selects the single-group kernel)
+int launch_edge_fwd_ws(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
+                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
+bool use_ws_kernels();
+bool use_ws_forward();
+
 // dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
 int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
                          const float* e_prev, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
@@ -417,7 +424,7 @@ int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float
                          cudaStream_t st) {
     const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
     if (math_mode != GCRL_MATH_FP32 && tc_ok)
-        return launch_edge_fwd_tc(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out,
+        return (use_ws_forward() ? launch_edge_fwd_ws : launch_edge_fwd_tc)(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out,
                                   agg, var, amin, amax, st);
     return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
 }

@@ -67,7 +67,9 @@ struct AggOut {
     const int32_t* seg_off;
 };
 
-__device__ __forceinline__ void agg_write(const AggOut& o, int32_t v, int col, const Stat& s) {
+// out of line: runs once per (segment, column) but is referenced from half a dozen places in the fused kernels,
+// whose hot loops have to fit the instruction cache
+static __device__ __noinline__ void agg_write(const AggOut& o, int32_t v, int col, const Stat& s) {
     int32_t deg = o.seg_off[v + 1] - o.seg_off[v];
     float mean, mn, mx, sd, var;
     stat_final(s, deg, mean, mn, mx, sd, var);
@@ -136,19 +138,85 @@ __device__ __forceinline__ void tile_reduce_scan_fn(LoadFn load, const int32_t* 
 // the 8 values of a group are loaded up front and segment boundaries come from a per-tile bit
 // mask (bit r set = row r starts a new destination), so no load sits on the branch chain.
 template <bool WANT_ARG>
+__device__ __forceinline__ void tile_reduce_scan_sw_t(const float* L, const int32_t* dst_s, const uint32_t* start_bits,
+                                                      int nrows, int32_t slot0, RedScratch* sc, const AggOut& out, int ltid);
+template <bool WANT_ARG>
 __device__ __forceinline__ void tile_reduce_scan_sw(const float* L, const int32_t* dst_s, const uint32_t* start_bits,
                                                     int nrows, int32_t slot0, RedScratch* sc, const AggOut& out) {
-    const int col = threadIdx.x & 63, q = threadIdx.x >> 6;
+    tile_reduce_scan_sw_t<WANT_ARG>(L, dst_s, start_bits, nrows, slot0, sc, out, (int)threadIdx.x);
+}
+// ltid: index of the thread inside the 256-thread reducer group
+template <bool WANT_ARG>
+__device__ __forceinline__ void tile_reduce_scan_sw_t(const float* L, const int32_t* dst_s, const uint32_t* start_bits,
+                                                      int nrows, int32_t slot0, RedScratch* sc, const AggOut& out, int ltid) {
+    const int col = ltid & 63, q = ltid >> 6;
     const int r0 = q * 32;
     const int r1 = min(r0 + 32, nrows);
     if (r0 >= r1) return;
     const int c4 = col >> 2, cc = c4 & 7;
     const unsigned char* base = reinterpret_cast<const unsigned char*>(L) + (c4 >> 3) * (128 * 128) + (col & 3) * 4;
     const uint32_t starts = start_bits[q] & ~1u;    // a boundary at the quarter's first row is the head itself
+    const int32_t hd = dst_s[r0];
+    const int nstart = __popc(starts);
+    if (nstart <= 1) {
+        // at most one segment boundary inside the quarter (always, for graphs of >= 34 vertices): rows [r0, ra) feed
+        // the head partial A, rows [ra, r1) the tail partial B; groups of 8 rows wholly on one side run straight-line
+        const int bl = nstart ? (__ffs(starts) - 1) : 32;
+        const int ra = min(r0 + bl, r1);
+        Stat A, B;
+        stat_init(A);
+        stat_init(B);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+            const int rb = r0 + 8 * g;
+            if (rb >= r1) break;
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = *reinterpret_cast<const float*>(base + (rb + k) * 128 + ((cc ^ k) << 4));
+            if (rb + 8 <= ra) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (WANT_ARG) stat_add(A, v[k], slot0 + rb + k);
+                    else stat_add_noarg(A, v[k]);
+                }
+            } else if (rb >= ra && rb + 8 <= r1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (WANT_ARG) stat_add(B, v[k], slot0 + rb + k);
+                    else stat_add_noarg(B, v[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = rb + k;
+                    if (r < ra) {
+                        if (WANT_ARG) stat_add(A, v[k], slot0 + r);
+                        else stat_add_noarg(A, v[k]);
+                    } else if (r < r1) {
+                        if (WANT_ARG) stat_add(B, v[k], slot0 + r);
+                        else stat_add_noarg(B, v[k]);
+                    }
+                }
+            }
+        }
+        sc->f[0][0][q][col] = A.sum; sc->f[0][1][q][col] = A.sq;
+        sc->f[0][2][q][col] = A.mn;  sc->f[0][3][q][col] = A.mx;
+        sc->a[0][0][q][col] = A.amn; sc->a[0][1][q][col] = A.amx;
+        const bool has_tail = nstart == 1 && r0 + bl < r1;
+        if (has_tail) {
+            sc->f[1][0][q][col] = B.sum; sc->f[1][1][q][col] = B.sq;
+            sc->f[1][2][q][col] = B.mn;  sc->f[1][3][q][col] = B.mx;
+            sc->a[1][0][q][col] = B.amn; sc->a[1][1][q][col] = B.amx;
+        }
+        if (col == 0) {
+            sc->head_dst[q] = hd;
+            sc->tail_dst[q] = has_tail ? dst_s[r0 + bl] : -1;
+        }
+        return;
+    }
     Stat cur;
     stat_init(cur);
-    int32_t cd = dst_s[r0];
-    const int32_t hd = cd;
+    int32_t cd = hd;
     bool seen = false;
 #pragma unroll 1
     for (int g = 0; g < 4; ++g) {
@@ -196,9 +264,12 @@ __device__ __forceinline__ void tile_reduce_scan(const float* M_s, int ld, const
 }
 
 // Phase B: threads 0..63 only (after a __syncthreads following phase A).
+__device__ __forceinline__ void tile_reduce_chain_t(int nrows, const RedScratch* sc, Carry& c, const AggOut& out, int col);
 __device__ __forceinline__ void tile_reduce_chain(int nrows, const RedScratch* sc, Carry& c,
                                                   const AggOut& out) {
-    const int col = threadIdx.x;
+    tile_reduce_chain_t(nrows, sc, c, out, (int)threadIdx.x);
+}
+__device__ __forceinline__ void tile_reduce_chain_t(int nrows, const RedScratch* sc, Carry& c, const AggOut& out, int col) {
     for (int q = 0; q < 4; ++q) {
         if (q * 32 >= nrows) break;
         Stat h;
@@ -223,10 +294,11 @@ __device__ __forceinline__ void tile_reduce_chain(int nrows, const RedScratch* s
     }
 }
 
-__device__ __forceinline__ void carry_flush(Carry& c, const AggOut& out) {
-    if (c.dst >= 0) agg_write(out, c.dst, threadIdx.x, c.s);
+__device__ __forceinline__ void carry_flush_t(Carry& c, const AggOut& out, int col) {
+    if (c.dst >= 0) agg_write(out, c.dst, col, c.s);
     c.dst = -1;
 }
+__device__ __forceinline__ void carry_flush(Carry& c, const AggOut& out) { carry_flush_t(c, out, (int)threadIdx.x); }
 
 // lower_bound over seg_off[0..N]: first v in [0,N] with seg_off[v] >= key, clamped to N
 __device__ __forceinline__ int32_t seg_lower_bound(const int32_t* __restrict__ seg_off, int32_t N,

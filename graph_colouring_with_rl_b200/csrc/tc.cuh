@@ -67,14 +67,16 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU
+// bounded wait: a protocol bug traps instead of hanging the GPU (out of line: the kernels have dozens of wait
+// sites and their code must stay inside the instruction cache)
+static __device__ __noinline__ void mbar_timeout_trap() {
+    printf("gcrl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("gcrl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
+        if (++spins > (1u << 22)) mbar_timeout_trap();      // try_wait itself sleeps up to its time hint
     }
 }
 
