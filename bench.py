@@ -286,10 +286,28 @@ def main():
             if k in bytes_per_edge:
                 kernels[k]['gbps'] = bytes_per_edge[k] * E_micro / (avg * 1e-3) / 1e9
     dom = max((k for k in kernels if k in bytes_per_edge), key=lambda k: kernels[k]['share_of_step'])
-    kname = {'edge_fwd_first': 'k_edge_fwd%s<first>', 'edge_fwd': 'k_edge_fwd%s', 'edge_fwd_last': 'k_edge_fwd%s<last>',
-             'edge_bwd_first': 'k_edge_bwd%s<first>', 'edge_bwd': 'k_edge_bwd%s', 'edge_bwd_last': 'k_edge_bwd%s<last>'}[dom] % ('' if args.math == 'fp32' else '_tc')
+    # which kernel serves each launch kind (gn_forward.cu / gn_backward.cu dispatch): the pipelined backward
+    # (k_edge_bwd_ws) for blocks 1-4, the single-group tensor-core kernels elsewhere
+    fwd_impl = '_ws' if os.environ.get('GCRL_FWD_IMPL', '') == 'ws' else '_tc'
+    bwd_impl = '_tc' if os.environ.get('GCRL_EDGE_IMPL', '') == 'tc' else '_ws'
+    if args.math == 'fp32':
+        fwd_impl = bwd_impl = ''
+    kname = {'edge_fwd_first': 'k_edge_fwd%s<first>' % fwd_impl, 'edge_fwd': 'k_edge_fwd%s' % fwd_impl,
+             'edge_fwd_last': 'k_edge_fwd%s<last>' % fwd_impl, 'edge_bwd_first': 'k_edge_bwd%s<first>' % bwd_impl,
+             'edge_bwd': 'k_edge_bwd%s' % bwd_impl,
+             'edge_bwd_last': 'k_edge_bwd%s<last>' % ('_tc' if args.math != 'fp32' else '')}[dom]
+    # DRAM traffic per launch: bytes per edge of this kernel from the committed `ncu --set full` capture
+    # (profiles/r01_traffic.json, dram__bytes_read.sum + dram__bytes_write.sum over the edges of that launch)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_traffic.json')))
+        ent = tj.get(args.math, {}).get(dom)
+        if ent:
+            traffic = ent['dram_bytes_per_edge'] * E_micro
+    except (OSError, ValueError):
+        pass
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': kernels[dom]['gbps'], 'peak': hbm_peak,
-                'unit': 'GB/s', 'frac': kernels[dom]['gbps'] / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'unit': 'GB/s', 'frac': kernels[dom]['gbps'] / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': bytes_per_edge[dom] * E_micro,
                 'share_of_step': kernels[dom]['share_of_step']}
 
