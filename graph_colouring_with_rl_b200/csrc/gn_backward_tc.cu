@@ -22,6 +22,7 @@
 // dz1) comes from G7 -- a handful of rows per tile instead of 128.
 // PNA backward uses per-vertex coefficient arrays (k_pna_bwd_coef):
 //   dm = d e_l + ca[v] + cb[v] * m + [slot == argmin] g_min + [slot == argmax] g_max.
+#define GCRL_MBAR_TIMEOUT   // counted waits (with a trap on protocol bugs): measurably faster here than the tight loop
 #include "gn_common.cuh"
 #include "tc.cuh"
 

@@ -78,11 +78,15 @@ struct BwdWsArgs {
 };
 
 // pipeline timeline of CTA 0 (GCRL_WS_TRACE=<file>): roles 0 TMA-E, 1 MMA, 2 TMA-MD, 3 WG_A, 4 WG_B, 5 WG_C, 6 WG_D
+#ifdef GCRL_WS_TRACE_BUILD
 #define WS_TR(on, role, tile, ev)                                                           \
     do {                                                                                    \
         if (a.trace && (on) && blockIdx.x == 0 && (tile) < 64)                              \
             a.trace[(((role) * 64 + (tile)) * 8) + (ev)] = clock64();                       \
     } while (0)
+#else
+#define WS_TR(on, role, tile, ev) do { } while (0)
+#endif
 
 template <bool FIRST, bool LAST, bool X3>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_constant__ CUtensorMap tm_e,
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 if (!FIRST) {
                     const uint32_t b1_hi = smem_u32(S.B1[s]);
                     if (elect_one()) {
-                        issue_gemm_feat<X3>(t_accA0 + 64 * (j % 3), b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
+                        issue_gemm_feat<X3, true>(t_accA0 + 64 * (j % 3), b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
                         umma_commit(&S.bar_acc1full[j % 3]);
                     }
                     __syncwarp();
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     mbar_wait(&S.bar_accBfree[s], ph ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
-                        issue_gemm_feat<X3>(t_accB0 + 64 * s, b2_hi, b2_lo, w2_hi, w2_lo, id_feat, false);
+                        issue_gemm_feat<X3, true>(t_accB0 + 64 * s, b2_hi, b2_lo, w2_hi, w2_lo, id_feat, false);
                         umma_commit(&S.bar_acc2full[s]);
                     }
                     __syncwarp();
@@ -263,8 +267,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 tc_fence_after();
                 WS_TR(lane == 0, 1, i, 1);
                 if (elect_one()) {
-                    issue_gemm_rows<X3>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
-                    issue_gemm_featT<X3>(t_accA0 + 64 * (i % 3), b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);
+                    issue_gemm_rows<X3, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
+                    issue_gemm_featT<X3, true>(t_accA0 + 64 * (i % 3), b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);
                     umma_commit(&S.bar_acc4full[i % 3]);
                 }
                 __syncwarp();
@@ -277,8 +281,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 tc_fence_after();
                 WS_TR(lane == 0, 1, i, 3);
                 if (elect_one()) {
-                    issue_gemm_rows<X3>(t_c, b2_hi, b2_lo, b1_hi, b1_hi + 16384, id_rows, 128, i > 0);
-                    if (!FIRST) issue_gemm_featT<X3>(t_accB0 + 64 * s, b2_hi, b2_lo, wc_hi, wc_lo, id_featT, false);
+                    issue_gemm_rows<X3, true>(t_c, b2_hi, b2_lo, b1_hi, b1_hi + 16384, id_rows, 128, i > 0);
+                    if (!FIRST) issue_gemm_featT<X3, true>(t_accB0 + 64 * s, b2_hi, b2_lo, wc_hi, wc_lo, id_featT, false);
                     umma_commit(&S.bar_acc6full[s]);
                     if (FIRST) umma_commit(&S.bar_B1free[s]);
                 }
@@ -325,13 +329,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             mbar_wait(&S.bar_accAfree[i % 3], ((i / 3) & 1) ^ 1);
             tc_fence_after();
             WS_TR(wtid == 0, 3, i, 0);
-#pragma unroll
+#pragma unroll 1
             for (int g = 0; g < 2; ++g) {
                 const int ra = 32 * q + 16 * g + (lane >> 2), rb = ra + 8;
-                const int32_t da = d4[2 * g], db = d4[2 * g + 1];
+                const int32_t da = g ? d4[2] : d4[0], db = g ? d4[3] : d4[1];
                 const bool va = da >= 0 && !(a.dbg & 2), vb = db >= 0 && !(a.dbg & 2);
-                const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)s4[2 * g] * 64 + cp);
-                const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)s4[2 * g + 1] * 64 + cp);
+                const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)(g ? s4[2] : s4[0]) * 64 + cp);
+                const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)(g ? s4[3] : s4[1]) * 64 + cp);
                 float2 ya[8], yb[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -452,20 +456,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             int32_t cur_v = -1;
             float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4;
             int k = 0;
-            for (int i = 0; i < n_cta; ++i) {
-                const int s = i & 1;
+            for (int i = 0; i <= n_cta; ++i) {               // iteration n_cta only runs epilogue 4 of the last tile
+                if (i > 0) epilogue4(i - 1);
+                if (i == n_cta) break;
                 const int32_t t0 = tile_t0(i);
                 const int nrows = min(TILE, a.E - t0);
-                // destination ids of this thread's 16 rows, in flight while waiting for B3
-                int32_t dv[16];
-#pragma unroll
-                for (int t = 0; t < 16; ++t) {
-                    const int R = 32 * (t >> 2) + (wtid >> 4) + 8 * (t & 3);
-                    dv[t] = R < nrows ? __ldg(a.dst + t0 + R) : -1;
-                }
                 if (i > 0) mbar_wait(&S.bar_acc4full[(i - 1) % 3], ((i - 1) / 3) & 1);    // G3/G4 of the previous tile read B3
                 WS_TR(wtid == 0, 4, i, 0);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     if (32 * j < nrows) {
                         const int slot = k % WS_NMD, u = k / WS_NMD;
@@ -478,7 +476,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                         for (int it = 0; it < 4; ++it) {
                             const int r = (wtid >> 4) + 8 * it;
                             const int R = 32 * j + r;
-                            const int32_t v = dv[4 * j + it];
+                            const int32_t v = R < nrows ? __ldg(a.dst + t0 + R) : -1;
                             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (v >= 0) {
                                 if (v != cur_v) {
@@ -510,9 +508,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 fence_proxy_async();
                 WS_TR(wtid == 0, 4, i, 5);
                 warp_arrive(&S.bar_B3full, lane);
-                if (i > 0) epilogue4(i - 1);
             }
-            epilogue4(n_cta - 1);
             atomicAdd(&S.bsum[4 * c4 + 0], bs0); atomicAdd(&S.bsum[4 * c4 + 1], bs1);
             atomicAdd(&S.bsum[4 * c4 + 2], bs2); atomicAdd(&S.bsum[4 * c4 + 3], bs3);
         } else {
@@ -644,7 +640,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 tmem_ld32(t_w2 + lane_addr + 32 * hh, v);
                 if (lane < 16)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(&a.gW2[o * 64 + 32 * hh + j], v[j]);
+                    for (int j = 0; j < 32; j += 4) red_add_v4(&a.gW2[o * 64 + 32 * hh + j], v[j], v[j + 1], v[j + 2], v[j + 3]);
                 tmem_ld32(t_c + lane_addr + 32 * hh, v);
                 if (lane < 16) {
                     if (!FIRST) {
@@ -702,17 +698,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                                 const float sum = warp_colsum32(acc, lane);
                                 atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * hf + lane, sum);
                             }
-                        } else if (nb == 1) {
-                            float part[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) part[j] = lane < bpos ? acc[j] : 0.f;
-                            const float sa = warp_colsum32(part, lane);
-                            atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * hf + lane, sa);
-                            tmem_ld32(t_acc + 32 * hf, acc);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) acc[j] = (lane >= bpos && ((hm >> j) & 1u)) ? acc[j] : 0.f;
-                            const float sb = warp_colsum32(acc, lane);
-                            atomicAdd(a.dPi + (int64_t)d1 * 64 + 32 * hf + lane, sb);
                         } else if (valid) {
                             float* pi = a.dPi + (int64_t)my_dst * 64 + 32 * hf;
 #pragma unroll

@@ -18,6 +18,7 @@
 // Shared memory per CTA ~110 KB (weights 32 KB, L 32 KB, B 32 KB, reducer 12 KB) so two CTAs share
 // an SM and hide each other's TMA / MMA latencies; TMEM: 128 columns per CTA.
 // Block 1 (edge_dim-wide input) skips steps 1-3: acc1 = C e is a few FMAs per element.
+#define GCRL_MBAR_TIMEOUT   // counted waits (with a trap on protocol bugs): measurably faster here than the tight loop
 #include "gn_common.cuh"
 #include "tc.cuh"
 

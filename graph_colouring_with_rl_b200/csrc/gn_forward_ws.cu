@@ -64,11 +64,15 @@ __device__ __forceinline__ long long clock_pinned() {      // not reordered acro
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory");
     return t;
 }
+#ifdef GCRL_WS_TRACE_BUILD
 #define FW_TR(on, role, tile, ev)                                                           \
     do {                                                                                    \
         if (a.trace && (on) && blockIdx.x == 0 && (tile) < 64)                              \
             a.trace[(((role) * 64 + (tile)) * 8) + (ev)] = clock_pinned();                  \
     } while (0)
+#else
+#define FW_TR(on, role, tile, ev) do { } while (0)
+#endif
 
 template <bool FIRST, bool X3, bool WANT_ARG>
 __global__ void __launch_bounds__(FW_THREADS, 1) k_edge_fwd_ws(const __grid_constant__ CUtensorMap tm_in,
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) k_edge_fwd_ws(const __grid_cons
             FW_TR(lane == 0, 1, j, 0);
             const uint32_t b1_hi = smem_u32(S.B1[s]);
             if (elect_one()) {
-                issue_gemm_feat<X3>(t_acc1 + 64 * (j % 3), b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
+                issue_gemm_feat<X3, true>(t_acc1 + 64 * (j % 3), b1_hi, b1_hi + 16384, wc_hi, wc_lo, id_feat, true);
                 umma_commit(&S.bar_acc1full[j % 3]);
                 umma_commit(&S.bar_B1free[s]);
             }
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) k_edge_fwd_ws(const __grid_cons
             tc_fence_after();
             FW_TR(lane == 0, 1, i, 1);
             if (elect_one()) {
-                issue_gemm_feat<X3>(t_acc2 + 64 * (i & 1), b2_hi, b2_lo, w2_hi, w2_lo, id_feat, false);
+                issue_gemm_feat<X3, true>(t_acc2 + 64 * (i & 1), b2_hi, b2_lo, w2_hi, w2_lo, id_feat, false);
                 umma_commit(&S.bar_acc2full[i & 1]);
             }
             __syncwarp();

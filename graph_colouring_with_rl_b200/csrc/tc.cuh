@@ -73,12 +73,25 @@ static __device__ __noinline__ void mbar_timeout_trap() {
     printf("gcrl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
+#ifdef GCRL_MBAR_TIMEOUT
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) mbar_timeout_trap();      // try_wait itself sleeps up to its time hint
     }
 }
+#else
+// production form: a three-instruction loop (the pipelined kernels are instruction-fetch bound: every wait site
+// counts).  Build with -DGCRL_MBAR_TIMEOUT to turn protocol bugs into traps instead of hangs.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra WAIT_LOOP;\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+#endif
 
 // ---- fences ----------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -223,46 +236,64 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
 
 // D[R x 64] (+)= A[R x 64] * B[64 x 64]^T contracting over the 64 columns (K-major operands):
 // 4 K=16 steps; X3 adds the lo*hi and hi*lo correction terms.  a_lo/b_lo ignored when !X3.
-template <bool X3>
+template <bool X3, bool ROLL = false>
 __device__ __forceinline__ void issue_gemm_feat(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                                 uint32_t b_lo, uint32_t idesc, bool accumulate_first) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    auto step = [&](int k) {
         const uint64_t ah = make_desc(a_hi + 32 * k, 16, 1024), bh = make_desc(b_hi + 32 * k, 16, 1024);
         umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
         if (X3) {
             umma_bf16(d_tmem, make_desc(a_lo + 32 * k, 16, 1024), bh, idesc, true);
             umma_bf16(d_tmem, ah, make_desc(b_lo + 32 * k, 16, 1024), idesc, true);
         }
+    };
+    if (ROLL) {
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) step(k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) step(k);
     }
 }
 // D[R x 64] (+)= A[R x 64] * W[64 x 64] (no transpose): A K-major, W read as an MN-major operand
 // (rows of the weight tile = contraction index): the B descriptor walks 16 rows (2048 bytes) per step.
-template <bool X3>
+template <bool X3, bool ROLL = false>
 __device__ __forceinline__ void issue_gemm_featT(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                                  uint32_t b_lo, uint32_t idesc, bool accumulate_first) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    auto step = [&](int k) {
         const uint64_t ah = make_desc(a_hi + 32 * k, 16, 1024), bh = make_desc(b_hi + 2048 * k, 8192, 1024);
         umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
         if (X3) {
             umma_bf16(d_tmem, make_desc(a_lo + 32 * k, 16, 1024), bh, idesc, true);
             umma_bf16(d_tmem, ah, make_desc(b_lo + 2048 * k, 8192, 1024), idesc, true);
         }
+    };
+    if (ROLL) {
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) step(k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) step(k);
     }
 }
 // D[64 x 64] (+)= A[rows x 64]^T * B[rows x 64] contracting over `rows` edge rows (MN-major
 // operands, M = N = 64): rows/16 K=16 steps, each advancing two 8-row groups (2048 bytes).
-template <bool X3>
+template <bool X3, bool ROLL = false>
 __device__ __forceinline__ void issue_gemm_rows(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                                 uint32_t b_lo, uint32_t idesc, int rows, bool accumulate_first) {
-    for (int k = 0; k < rows / 16; ++k) {
+    auto step = [&](int k) {
         const uint64_t ah = make_desc(a_hi + 2048 * k, 8192, 1024), bh = make_desc(b_hi + 2048 * k, 8192, 1024);
         umma_bf16(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
         if (X3) {
             umma_bf16(d_tmem, make_desc(a_lo + 2048 * k, 8192, 1024), bh, idesc, true);
             umma_bf16(d_tmem, ah, make_desc(b_lo + 2048 * k, 8192, 1024), idesc, true);
         }
+    };
+    if (ROLL) {
+#pragma unroll 1
+        for (int k = 0; k < rows / 16; ++k) step(k);
+    } else {
+        for (int k = 0; k < rows / 16; ++k) step(k);
     }
 }
 
