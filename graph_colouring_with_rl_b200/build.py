@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(PKG_DIR, 'libgcrl_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden',
-          '--expt-relaxed-constexpr', '-Xptxas', '-v']
+          '--expt-relaxed-constexpr', '-Xptxas', '-v'] + os.environ.get('GCRL_NVCC_FLAGS', '').split()
+# GCRL_NVCC_FLAGS: extra flags for diagnostic builds, e.g. -DGCRL_WS_TRACE_BUILD (pipeline timeline of CTA 0 of the
+# warp-specialised kernels, dumped when GCRL_WS_TRACE=<file> is set) or -DGCRL_MBAR_TIMEOUT (trap on a stuck mbarrier)
 
 
 def sources():

@@ -13,6 +13,7 @@
 //   HBM traffic per edge: read e_{l-1}, e_l, d e_l; write d e_{l-1} (1 KB fp32); block 5
 //   recomputes e_5 instead of reading it, block 1 writes no d e_0.
 #include "gn_common.cuh"
+#include <stdlib.h>
 
 namespace gcrl {
 
@@ -641,9 +642,10 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             // the pipelined kernel takes the arg-min/max terms pre-added to d e_l (a workspace buffer
             // nobody else reads); block 5 has no d e_l and applies them itself
             // block 5 (e_5 recomputed in-kernel: a longer per-tile chain) is still faster on the single-group kernel
-            const bool ws = use_ws_kernels() && de_cur != nullptr;
-            float* de_scatter = ws ? const_cast<float*>(de_cur) : nullptr;
-            float* gb2_vertex = nullptr;     // (only the pipelined kernel's block-5 variant takes db2 from here)
+            static const bool ws_last = getenv("GCRL_BWD_LAST_WS") != nullptr;       // experiment: block 5 on the pipelined kernel
+            const bool ws = use_ws_kernels() && (de_cur != nullptr || ws_last);
+            float* de_scatter = (ws && de_cur) ? const_cast<float*>(de_cur) : nullptr;
+            float* gb2_vertex = (ws && !de_cur) ? G(b.b2) : nullptr;     // the pipelined kernel's block-5 variant takes db2 from here
             RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
                                    gb2_vertex, st));
             RC((ws ? launch_edge_bwd_ws : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],

@@ -457,8 +457,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4;
             int k = 0;
             for (int i = 0; i <= n_cta; ++i) {               // iteration n_cta only runs epilogue 4 of the last tile
-                if (i > 0) epilogue4(i - 1);
-                if (i == n_cta) break;
+              if (i < n_cta) {                               // dm(i) first: it only needs G3/G4 of tile i-1 ...
                 const int32_t t0 = tile_t0(i);
                 const int nrows = min(TILE, a.E - t0);
                 if (i > 0) mbar_wait(&S.bar_acc4full[(i - 1) % 3], ((i - 1) / 3) & 1);    // G3/G4 of the previous tile read B3
@@ -508,6 +507,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 fence_proxy_async();
                 WS_TR(wtid == 0, 4, i, 5);
                 warp_arrive(&S.bar_B3full, lane);
+              }
+                if (i > 0) epilogue4(i - 1);                 // ... epilogue 4 of tile i-1 needs its G5/G6
             }
             atomicAdd(&S.bsum[4 * c4 + 0], bs0); atomicAdd(&S.bsum[4 * c4 + 1], bs1);
             atomicAdd(&S.bsum[4 * c4 + 2], bs2); atomicAdd(&S.bsum[4 * c4 + 3], bs3);
@@ -785,7 +786,7 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
     a.m = m; a.de = de; a.trace = nullptr;
     {
         static int pf = -1;
-        if (pf < 0) { const char* e = getenv("GCRL_WS_PF"); pf = e ? atoi(e) : 0; }
+        if (pf < 0) { const char* e = getenv("GCRL_WS_PF"); pf = e ? atoi(e) : 1; }
         a.pf = pf;
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; }
