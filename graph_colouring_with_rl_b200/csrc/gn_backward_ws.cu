@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
         for (int i = 0; i < 2; ++i) {
             mbar_init(&S.bar_B1full[i], 4);
             mbar_init(&S.bar_B1free[i], 1);
-            mbar_init(&S.bar_accBfree[i], 4);
+            mbar_init(&S.bar_accBfree[i], LAST ? 4 : 8);      // epilogue 4: WG_B (block 5) or the two WG_C groups
             mbar_init(&S.bar_acc2full[i], 1);
             mbar_init(&S.bar_acc6full[i], 1);
-            mbar_init(&S.bar_OUTfull[i], 4);
+            mbar_init(&S.bar_OUTfull[i], LAST ? 4 : 8);
         }
         for (int i = 0; i < 3; ++i) { mbar_init(&S.bar_accAfree[i], 12); mbar_init(&S.bar_acc1full[i], 1); mbar_init(&S.bar_acc4full[i], 1); }
         mbar_init(&S.bar_B2full, 8);
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
         // ================= WG_B: dm operand tile; epilogue 4 (d e_{l-1} = acc6 -> fp32 staging in the dead B1[s]) ====
         unsigned char* b3 = S.B3;
         auto epilogue4 = [&](int i) {
-            if (FIRST) return;
+            if (FIRST || !LAST) return;       // blocks 1-4: done by the WG_C groups
             const int s = i & 1, ph = (i >> 1) & 1;
             const int row = 32 * q + lane;
             float* out = reinterpret_cast<float*>(S.B1[s]);
@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             int32_t cur_v = -1;
             float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4;
             int k = 0;
-            for (int i = 0; i <= n_cta; ++i) {               // iteration n_cta only runs epilogue 4 of the last tile
-              if (i < n_cta) {                               // dm(i) first: it only needs G3/G4 of tile i-1 ...
+            for (int i = 0; i < n_cta; ++i) {
+              {
                 const int32_t t0 = tile_t0(i);
                 const int nrows = min(TILE, a.E - t0);
                 if (i > 0) mbar_wait(&S.bar_acc4full[(i - 1) % 3], ((i - 1) / 3) & 1);    // G3/G4 of the previous tile read B3
@@ -508,7 +508,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 WS_TR(wtid == 0, 4, i, 5);
                 warp_arrive(&S.bar_B3full, lane);
               }
-                if (i > 0) epilogue4(i - 1);                 // ... epilogue 4 of tile i-1 needs its G5/G6
             }
             atomicAdd(&S.bsum[4 * c4 + 0], bs0); atomicAdd(&S.bsum[4 * c4 + 1], bs1);
             atomicAdd(&S.bsum[4 * c4 + 2], bs2); atomicAdd(&S.bsum[4 * c4 + 3], bs3);
@@ -577,6 +576,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
         const bool tr = (tid == 12 * 32);
         __nv_bfloat16* b2h = reinterpret_cast<__nv_bfloat16*>(S.B2);
         __nv_bfloat16* b2l = reinterpret_cast<__nv_bfloat16*>(S.B2 + 16384);
+        // epilogue 4 of tile j, this group's 32 columns: d e_{l-1} = acc6 -> fp32 staging slab in the dead B1[j & 1]
+        auto epilogue4_half = [&](int j) {
+            if (FIRST || LAST) return;
+            const int sj = j & 1;
+            float* out = reinterpret_cast<float*>(S.B1[sj]);
+            mbar_wait(&S.bar_acc6full[sj], (j >> 1) & 1);      // G5 has finished with B1[sj], G6 wrote ACC_B[sj]
+            tc_fence_after();
+            float acc[32];
+            tmem_ld32(t_accB0 + 64 * sj + lane_addr + 32 * half, acc);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(l_ptr(out, row, 8 * half + c)) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            tc_fence_before();
+            fence_proxy_async();
+            warp_arrive(&S.bar_accBfree[sj], lane);
+            warp_arrive(&S.bar_OUTfull[sj], lane);     // warp 3 issues the TMA store
+        };
         for (int i = 0; i < n_cta; ++i) {
             const int s = i & 1, ph = (i >> 1) & 1;
             const int a3 = i % 3, pa = (i / 3) & 1;
@@ -609,6 +625,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             tc_fence_before();
             WS_TR(tr, 5, i, 2);
             warp_arrive(&S.bar_B2full, lane);
+            if (i > 0) epilogue4_half(i - 1);          // while G3/G4 of this tile run
             // ---- epilogue 3: dz1 = d hid * relu' -> B2 (G3/G4 have finished with hid) -----------------------------------
             mbar_wait(&S.bar_acc4full[a3], pa);
             tc_fence_after();
@@ -630,6 +647,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             warp_arrive(&S.bar_dz1full, lane);
             warp_arrive(&S.bar_accAfree[a3], lane);
         }
+        epilogue4_half(n_cta - 1);
         // ---- weight gradients: TMEM -> global (one atomic pass per CTA) ----------------------------------------------------
         mbar_wait(&S.bar_done, 0);
         tc_fence_after();
