@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) k_edge_fwd_ws(const __grid_cons
                                         S.red.a[0][0][qtr][col] = cur.amn; S.red.a[0][1][qtr][col] = cur.amx;
                                         seen = true;
                                     } else {
-                                        agg_write(a.out, cd, col, cur);
+                                        agg_write_ool(a.out, cd, col, cur);
                                     }
                                     stat_init(cur);
                                     cd = __shfl_sync(0xffffffffu, d, 8 * g + k);
@@ -539,12 +539,12 @@ __global__ void __launch_bounds__(FW_THREADS, 1) k_edge_fwd_ws(const __grid_cons
                     if (carry.dst == hdq) {
                         stat_merge(carry.s, h);
                     } else {
-                        if (carry.dst >= 0) agg_write(a.out, carry.dst, col, carry.s);
+                        if (carry.dst >= 0) agg_write_ool(a.out, carry.dst, col, carry.s);
                         carry.s = h; carry.dst = hdq;
                     }
                     const int32_t tdq = td[qq];
                     if (tdq >= 0) {
-                        agg_write(a.out, carry.dst, col, carry.s);
+                        agg_write_ool(a.out, carry.dst, col, carry.s);
                         carry.s.sum = S.red.f[1][0][qq][col]; carry.s.sq = S.red.f[1][1][qq][col];
                         carry.s.mn = S.red.f[1][2][qq][col];  carry.s.mx = S.red.f[1][3][qq][col];
                         carry.s.amn = S.red.a[1][0][qq][col]; carry.s.amx = S.red.a[1][1][qq][col];

@@ -67,9 +67,7 @@ struct AggOut {
     const int32_t* seg_off;
 };
 
-// out of line: runs once per (segment, column) but is referenced from half a dozen places in the fused kernels,
-// whose hot loops have to fit the instruction cache
-static __device__ __noinline__ void agg_write(const AggOut& o, int32_t v, int col, const Stat& s) {
+__device__ __forceinline__ void agg_write(const AggOut& o, int32_t v, int col, const Stat& s) {
     int32_t deg = o.seg_off[v + 1] - o.seg_off[v];
     float mean, mn, mx, sd, var;
     stat_final(s, deg, mean, mn, mx, sd, var);
@@ -79,6 +77,9 @@ static __device__ __noinline__ void agg_write(const AggOut& o, int32_t v, int co
     if (o.amin) o.amin[(int64_t)v * 64 + col] = s.amn;
     if (o.amax) o.amax[(int64_t)v * 64 + col] = s.amx;
 }
+// out-of-line copy for the warp-specialised kernels, whose hot loops have to fit the instruction cache (it runs
+// once per (segment, column) but is referenced from several places)
+static __device__ __noinline__ void agg_write_ool(const AggOut& o, int32_t v, int col, const Stat& s) { agg_write(o, v, col, s); }
 
 // scratch carved from shared memory: 2 (head/tail) x 6 fields x 4 quarters x 64 cols + ids
 struct RedScratch {
