@@ -16,6 +16,7 @@
 // starts in [w*ITEM_EDGES, (w+1)*ITEM_EDGES) -- whole segments, found by binary search on
 // seg_off, so no cross-CTA combination and no atomics.  Persistent CTAs stride over items.
 #include "gn_common.cuh"
+#include <stdlib.h>
 
 namespace gcrl {
 
@@ -463,6 +464,11 @@ int launch_node_update(const NetW& net, int l /*0-based*/, bool with_extra, cons
     return GCRL_OK;
 }
 
+// gn_node_tc.cu
+int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, float* agg, const float* h_in,
+                          const int32_t* seg_off, int64_t N, float* h_out, float* Pi, float* Pj, float* q,
+                          float* u1_buf, float* y1_buf, float* y2_buf, cudaStream_t st);
+
 }  // namespace gcrl
 
 using namespace gcrl;
@@ -541,6 +547,13 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         if (rc) return rc;
         float* Pin = (stash_p && !last) ? S.Pi[l + 1] : Pi;
         float* Pjn = (stash_p && !last) ? S.Pj[l + 1] : Pj;
+        const int Dv_l = net.blk[l].Dv;
+        static const bool node_ffma = getenv("GCRL_NODE_IMPL") && getenv("GCRL_NODE_IMPL")[0] == 'f';   // A/B switch
+        if (math_mode != GCRL_MATH_FP32 && gdim == 0 && (Dv_l == 64 || Dv_l <= 8) && !node_ffma) {
+            // tensor-core vertex side; without a stash the (dead) projection buffers of this block serve as scratch
+            rc = launch_node_update_tc(net, l, true, math_mode == GCRL_MATH_BF16X3, agg, h_prev, seg_off, N, hl, Pin, Pjn, q_out,
+                                       stash_p ? S.u1[l] : Pi, stash_p ? S.y1 : Pi, stash_p ? S.y2 : Pj, st);
+        } else
         rc = launch_node_update(net, l, true, agg, h_prev, seg_off, gfeat, vgraph, N, hl, Pin, Pjn, q_out,
                                 stash_p ? S.u1[l] : nullptr, (stash_p && last) ? S.y1 : nullptr,
                                 (stash_p && last) ? S.y2 : nullptr, st);

@@ -1,0 +1,319 @@
+// gn_node_tc.cu -- vertex side of the GN forward pass on the tensor cores (math modes bf16 / bf16x3).
+//
+// GNNBlock.update (architecture.py:68-78: MLP([aggr | x]) with Linear -> ReLU -> Linear), the next block's
+// per-vertex projections Pi = A h + b1, Pj = B h (the algebraic split of message_mlp.0, gn_forward.cu) and the
+// fc1/fc2/fc3 head (architecture.py:191-197) are chains of row-GEMMs  out[N, 64 or 128] = act([A1 | A2] W^T + b).
+// k_rows_gemm_tc runs one such GEMM: 128-vertex tiles, the K = 64-column chunks of A1 / A2 arrive by TMA (fp32,
+// SWIZZLE_128B), are split into bf16 hi/lo operand tiles and accumulated in TMEM by tcgen05.mma; the epilogue adds
+// the bias (and the K < 64 tail of block 1, whose vertex features are 2 wide), applies ReLU and leaves through a
+// TMA store.  The fp32 FFMA kernel k_node_update (gn_forward.cu) stays the parity path of math mode fp32; on the
+// 10 000 x 50-vertex rollout batch it was 29 % of a step (2.05 ms per block, 16 TFLOP/s of FFMA behind 12 LDS per
+// 32 FMA).
+#define GCRL_MBAR_TIMEOUT
+#include "gn_common.cuh"
+#include "tc.cuh"
+
+namespace gcrl {
+
+using namespace tc;
+
+struct RowsGemmArgs {
+    const float* W0; int ldW0, col0;       // weights of output columns [0, 64): element (o, k) = W0[o * ldW0 + col0 + k]
+    const float* W1; int ldW1, col1;       // output columns [64, 128) (NOUT = 128)
+    const float* bias0; const float* bias1;   // [64] or null
+    int relu;
+    int n1, n2;                            // 64-column chunks taken from tensor map 1 / tensor map 2
+    const float* xt; int Dt;               // tail: out0[:, o] += sum_{d < Dt} Wt[o * ldWt + colt + d] * xt[row * Dt + d]
+    const float* Wt; int ldWt, colt;
+    int64_t N;
+};
+
+constexpr int NODE_MAX_CHUNKS = 5;
+
+template <int NOUT, bool X3>
+__global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__ CUtensorMap tm1,
+                                                        const __grid_constant__ CUtensorMap tm2,
+                                                        const __grid_constant__ CUtensorMap tmo0,
+                                                        const __grid_constant__ CUtensorMap tmo1, const RowsGemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int nch = a.n1 + a.n2;
+    constexpr int WCH = (NOUT / 64) * 16384;                  // bytes of one weight chunk: hi [NOUT x 64] | lo [NOUT x 64]
+    unsigned char* Wsm = base;                                // [nch][WCH]
+    float* L0 = reinterpret_cast<float*>(base + nch * WCH);   // landing / staging tiles (fp32 SW128 slabs)
+    float* L1 = L0 + 128 * 64;
+    unsigned char* Aop = reinterpret_cast<unsigned char*>(L1 + 128 * 64);   // operand tile hi | lo
+    float* bias_s = reinterpret_cast<float*>(Aop + 32768);    // [128]
+    float* wt_s = bias_s + 128;                               // [64][8] tail weights
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wt_s + 64 * 8);
+    uint64_t* bar_tma = bars;                                 // [2]
+    uint64_t* bar_mma = bars + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sp = warp & 3, half = warp >> 2;
+    const int row = 32 * sp + lane;
+    if (tid == 0) {
+        mbar_init(&bar_tma[0], 1);
+        mbar_init(&bar_tma[1], 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    for (int c = 0; c < nch; ++c) {
+        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH);
+        __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH + WCH / 2);
+        load_weight_tile(a.W0, a.ldW0, a.col0 + 64 * c, hi, lo, tid, 256);
+        if (NOUT == 128) load_weight_tile(a.W1, a.ldW1, a.col1 + 64 * c, hi + 64 * 64, lo + 64 * 64, tid, 256);
+    }
+    if (tid < 128) bias_s[tid] = tid < 64 ? (a.bias0 ? a.bias0[tid] : 0.f) : ((NOUT == 128 && a.bias1) ? a.bias1[tid - 64] : 0.f);
+    for (int t = tid; t < 64 * 8; t += 256) {
+        const int o = t >> 3, d = t & 7;
+        wt_s[t] = (a.Dt > 0 && d < a.Dt) ? a.Wt[o * a.ldWt + a.colt + d] : 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = (uint32_t)(32 * sp) << 16;
+    const uint32_t idesc = make_idesc_bf16(128, NOUT, false, false);
+    uint32_t ph_tma[2] = {0u, 0u}, ph_mma = 0u;
+
+    auto issue_load = [&](int c, int32_t v0) {          // chunk c of the tile starting at row v0 -> landing buffer c & 1
+        float* L = (c & 1) ? L1 : L0;
+        const CUtensorMap* tm = c < a.n1 ? &tm1 : &tm2;
+        const int col = 64 * (c < a.n1 ? c : c - a.n1);
+        mbar_arrive_expect_tx(&bar_tma[c & 1], 128 * 64 * 4);
+        tma_load_2d(L, tm, col, v0, &bar_tma[c & 1]);
+        tma_load_2d(L + 128 * 32, tm, col + 32, v0, &bar_tma[c & 1]);
+    };
+
+    const int64_t n_tiles = (a.N + 127) / 128;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int32_t v0 = (int32_t)(tile * 128);
+        if (tid == 0) {
+            issue_load(0, v0);
+            if (nch > 1) issue_load(1, v0);
+        }
+        for (int c = 0; c < nch; ++c) {
+            const float* L = (c & 1) ? L1 : L0;
+            mbar_wait(&bar_tma[c & 1], ph_tma[c & 1]);
+            ph_tma[c & 1] ^= 1u;
+            if (c > 0) {                                 // the previous chunk's MMA has read the operand tile
+                mbar_wait(bar_mma, ph_mma);
+                ph_mma ^= 1u;
+            }
+            convert_tile128<X3>(L, reinterpret_cast<__nv_bfloat16*>(Aop), reinterpret_cast<__nv_bfloat16*>(Aop + 16384), tid);
+            fence_proxy_async();
+            __syncthreads();                             // operand tile complete; landing buffer c & 1 is free again
+            if (warp == 0 && elect_one()) {
+                if (c + 2 < nch) issue_load(c + 2, v0);
+                tc_fence_after();
+                const uint32_t w_hi = smem_u32(Wsm + c * WCH);
+                issue_gemm_feat<X3>(tmem, smem_u32(Aop), smem_u32(Aop) + 16384, w_hi, w_hi + WCH / 2, idesc, c > 0);
+                umma_commit(bar_mma);
+            }
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: bias (+ tail) (+ relu) -> fp32 staging tiles (L0: outputs 0-63, L1: outputs 64-127) ----------------
+        const bool valid = v0 + row < a.N;
+        float xt[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) xt[d] = (valid && d < a.Dt) ? a.xt[(int64_t)(v0 + row) * a.Dt + d] : 0.f;
+        constexpr int PASSES = NOUT / 64;               // 32-column passes per warp
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            // NOUT = 64: warp half h owns columns [32h, 32h+32); NOUT = 128: half h owns output matrix h, two passes
+            const int col0 = NOUT == 64 ? 32 * half : 64 * half + 32 * p;
+            float acc[32];
+            tmem_ld32(tmem + lane_addr + col0, acc);
+            float* Lout = (NOUT == 128 && half == 1) ? L1 : L0;
+            const int lc0 = col0 & 63;                  // column inside the 64-wide staging tile
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int o = col0 + 4 * c + j;
+                    float x = acc[4 * c + j] + bias_s[o];
+                    if (a.Dt > 0 && o < 64) {
+#pragma unroll
+                        for (int d = 0; d < 8; ++d) x = fmaf(wt_s[o * 8 + d], xt[d], x);
+                    }
+                    v[j] = a.relu ? fmaxf(x, 0.f) : x;
+                }
+                *reinterpret_cast<float4*>(l_ptr(Lout, row, (lc0 >> 2) + c)) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&tmo0, 0, v0, L0);             // rows past N are clipped by the tensor map
+            tma_store_2d(&tmo0, 32, v0, L0 + 128 * 32);
+            if (NOUT == 128) {
+                tma_store_2d(&tmo1, 0, v0, L1);
+                tma_store_2d(&tmo1, 32, v0, L1 + 128 * 32);
+            }
+            bulk_commit();
+            bulk_wait_read0();
+        }
+        __syncthreads();                                 // staging tiles are free for the next tile's loads
+    }
+    if (tid == 0) bulk_wait0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+// host side: tensor map of a row-major fp32 matrix [rows, cols] (cols a multiple of 32), box {32, 128}
+static int make_tmap_rows(CUtensorMap* out, const float* basep, int64_t rows, int cols);
+
+template <int NOUT, bool X3>
+static int launch_rows_gemm(const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& o0, const CUtensorMap& o1,
+                            const RowsGemmArgs& a, cudaStream_t st) {
+    const int nch = a.n1 + a.n2;
+    const int smem = nch * (NOUT / 64) * 16384 + 2 * 32768 + 32768 + 128 * 4 + 64 * 8 * 4 + 64 + 1024;
+    static int max_set = 0;
+    if (smem > max_set) {
+        GCRL_CUDA(cudaFuncSetAttribute(k_rows_gemm_tc<NOUT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set = smem;
+    }
+    int64_t tiles = (a.N + 127) / 128;
+    int64_t grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    k_rows_gemm_tc<NOUT, X3><<<(int)grid, 256, smem, st>>>(t1, t2, o0, o1, a);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap_rows(CUtensorMap* out, const float* basep, int64_t rows, int cols) {
+    static EncodeTiledFn2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn2)p;
+    }
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return GCRL_ERR_CUDA;
+    }
+    if (rows < 1) rows = 1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(basep), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%lld cols=%d", (int)r, (const void*)basep, (long long)rows, cols);
+        return GCRL_ERR_CUDA;
+    }
+    return GCRL_OK;
+}
+
+// agg rows of vertices without incoming edges take the scatter defaults (0, 0, 0, sqrt(eps)): the edge kernel never
+// visits them (principal_neighbourhood_aggregation.py:45-64 on an empty segment)
+__global__ void k_fix_empty_agg(float* __restrict__ agg, const int32_t* __restrict__ seg_off, int64_t N) {
+    const int64_t total = N * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = t >> 6;
+        const int c4 = (int)(t & 63);
+        if (seg_off[v + 1] == seg_off[v]) {
+            const float s = c4 >= 48 ? sqrtf(PNA_EPS) : 0.f;
+            reinterpret_cast<float4*>(agg + v * 256)[c4] = make_float4(s, s, s, s);
+        }
+    }
+}
+
+// q[v] = y2[v, :] . F3 + f3
+__global__ void k_head_dot(const float* __restrict__ y2, const float* __restrict__ F3, const float* __restrict__ f3,
+                           int64_t N, float* __restrict__ q) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float w0 = F3[lane], w1 = F3[32 + lane], b = f3[0];
+    for (int64_t v = warp0; v < N; v += nwarps) {
+        float s = y2[v * 64 + lane] * w0 + y2[v * 64 + 32 + lane] * w1;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) q[v] = s + b;
+    }
+}
+
+// Tensor-core vertex update; same contract as launch_node_update (gn_forward.cu) for Dg == 0 and Dv == 64 or Dv <= 8.
+// u1_buf / y1_buf / y2_buf: [N,64] outputs (stash) or scratch.
+int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, float* agg, const float* h_in,
+                          const int32_t* seg_off, int64_t N, float* h_out, float* Pi, float* Pj, float* q,
+                          float* u1_buf, float* y1_buf, float* y2_buf, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    const BlockW& b = net.blk[l];
+    const bool last = with_extra && (l == GCRL_N_BLOCKS - 1);
+    int rc;
+    {
+        int64_t blocks = (N * 64 + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+        k_fix_empty_agg<<<(int)blocks, 256, 0, st>>>(agg, seg_off, N);
+        GCRL_LAUNCH_CHECK();
+    }
+    CUtensorMap t_agg, t_h, t_u1, t_ho, t_pi, t_pj, t_y1, t_y2;
+    if ((rc = make_tmap_rows(&t_agg, agg, N, 256))) return rc;
+    if ((rc = make_tmap_rows(&t_u1, u1_buf, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&t_ho, h_out, N, 64))) return rc;
+    const bool wide_h = b.Dv == 64;
+    if ((rc = make_tmap_rows(&t_h, wide_h ? h_in : u1_buf, N, 64))) return rc;
+    const int K1 = 256 + b.Dv;
+    RowsGemmArgs a;
+    // update_mlp.0 + ReLU
+    a.W0 = b.U1; a.ldW0 = K1; a.col0 = 0; a.W1 = nullptr; a.ldW1 = 0; a.col1 = 0;
+    a.bias0 = b.c1; a.bias1 = nullptr; a.relu = 1;
+    a.n1 = 4; a.n2 = wide_h ? 1 : 0;
+    a.xt = wide_h ? nullptr : h_in; a.Dt = wide_h ? 0 : b.Dv; a.Wt = b.U1; a.ldWt = K1; a.colt = 256;
+    a.N = N;
+    rc = x3 ? launch_rows_gemm<64, true>(t_agg, t_h, t_u1, t_u1, a, st) : launch_rows_gemm<64, false>(t_agg, t_h, t_u1, t_u1, a, st);
+    if (rc) return rc;
+    // update_mlp.2
+    a.W0 = b.U2; a.ldW0 = 64; a.col0 = 0; a.bias0 = b.c2; a.relu = 0; a.n1 = 1; a.n2 = 0; a.xt = nullptr; a.Dt = 0;
+    rc = x3 ? launch_rows_gemm<64, true>(t_u1, t_u1, t_ho, t_ho, a, st) : launch_rows_gemm<64, false>(t_u1, t_u1, t_ho, t_ho, a, st);
+    if (rc) return rc;
+    if (!with_extra) return GCRL_OK;
+    if (!last) {
+        // next block's projections: Pi = A h + b1, Pj = B h  (one N = 128 product)
+        const BlockW& nb = net.blk[l + 1];
+        const int ldn = 2 * nb.Dv + nb.De;
+        if ((rc = make_tmap_rows(&t_pi, Pi, N, 64))) return rc;
+        if ((rc = make_tmap_rows(&t_pj, Pj, N, 64))) return rc;
+        a.W0 = nb.W1; a.ldW0 = ldn; a.col0 = 0; a.W1 = nb.W1; a.ldW1 = ldn; a.col1 = 64;
+        a.bias0 = nb.b1; a.bias1 = nullptr; a.relu = 0; a.n1 = 1; a.n2 = 0;
+        rc = x3 ? launch_rows_gemm<128, true>(t_ho, t_ho, t_pi, t_pj, a, st) : launch_rows_gemm<128, false>(t_ho, t_ho, t_pi, t_pj, a, st);
+        return rc;
+    }
+    // head: fc1 + ReLU, fc2 + ReLU, fc3
+    if ((rc = make_tmap_rows(&t_y1, y1_buf, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&t_y2, y2_buf, N, 64))) return rc;
+    a.W0 = net.head.F1; a.ldW0 = 64; a.col0 = 0; a.W1 = nullptr; a.bias0 = net.head.f1; a.bias1 = nullptr; a.relu = 1; a.n1 = 1; a.n2 = 0;
+    rc = x3 ? launch_rows_gemm<64, true>(t_ho, t_ho, t_y1, t_y1, a, st) : launch_rows_gemm<64, false>(t_ho, t_ho, t_y1, t_y1, a, st);
+    if (rc) return rc;
+    a.W0 = net.head.F2; a.bias0 = net.head.f2;
+    rc = x3 ? launch_rows_gemm<64, true>(t_y1, t_y1, t_y2, t_y2, a, st) : launch_rows_gemm<64, false>(t_y1, t_y1, t_y2, t_y2, a, st);
+    if (rc) return rc;
+    {
+        int64_t blocks = (N * 32 + 255) / 256;
+        if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+        k_head_dot<<<(int)blocks, 256, 0, st>>>(y2_buf, net.head.F3, net.head.f3, N, q);
+        GCRL_LAUNCH_CHECK();
+    }
+    return GCRL_OK;
+}
+
+}  // namespace gcrl
