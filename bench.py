@@ -275,8 +275,11 @@ def main():
 
     # ---- roofline of the dominant kernel (edge backward, blocks 2-4) -------------------------------------
     kinds = ['edge_fwd_first', 'edge_fwd', 'edge_fwd_last', 'edge_bwd_first', 'edge_bwd', 'edge_bwd_last', 'pna_fwd', 'pna_bwd']
+    # block 5: the tensor-core modes stash e_5 (forward writes it: counted under edge_fwd) and its backward then reads
+    # e_4, e_5 and writes d e_4 (768 B/edge); the recompute flavour (fp32, GCRL_EDGE_IMPL=tc) reads e_4, writes d e_4
+    recompute_e5 = args.math == 'fp32' or os.environ.get('GCRL_EDGE_IMPL', '') == 'tc'
     bytes_per_edge = {'edge_fwd_first': 4 + 256, 'edge_fwd': 512, 'edge_fwd_last': 256, 'edge_bwd_first': 4 + 512,
-                      'edge_bwd': 1024, 'edge_bwd_last': 512}
+                      'edge_bwd': 1024, 'edge_bwd_last': 512 if recompute_e5 else 768}
     E_micro = min(args.micro_graphs, G) * n * (n - 1)
     kernels = {}
     for i, k in enumerate(kinds):
@@ -295,7 +298,7 @@ def main():
     kname = {'edge_fwd_first': 'k_edge_fwd%s<first>' % fwd_impl, 'edge_fwd': 'k_edge_fwd%s' % fwd_impl,
              'edge_fwd_last': 'k_edge_fwd%s<last>' % fwd_impl, 'edge_bwd_first': 'k_edge_bwd%s<first>' % bwd_impl,
              'edge_bwd': 'k_edge_bwd%s' % bwd_impl,
-             'edge_bwd_last': 'k_edge_bwd%s<last>' % ('_tc' if args.math != 'fp32' else '')}[dom]
+             'edge_bwd_last': 'k_edge_bwd%s<block 5>' % bwd_impl}[dom]
     # DRAM traffic per launch: bytes per edge of this kernel from the committed `ncu --set full` capture
     # (profiles/r01_traffic.json, dram__bytes_read.sum + dram__bytes_write.sum over the edges of that launch)
     traffic = None

@@ -642,15 +642,16 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             // the pipelined kernel takes the arg-min/max terms pre-added to d e_l (a workspace buffer
             // nobody else reads); block 5 has no d e_l and applies them itself
             // block 5 (e_5 recomputed in-kernel: a longer per-tile chain) is still faster on the single-group kernel
-            static const bool ws_last = getenv("GCRL_BWD_LAST_WS") != nullptr;       // experiment: block 5 on the pipelined kernel
-            const bool ws = use_ws_kernels() && (de_cur != nullptr || ws_last);
+            // block 5 has no d e_5: with e_5 stashed by the forward it runs as a regular pipelined block (dm without the
+            // d e_l term); GCRL_EDGE_IMPL=tc recomputes e_5 in the single-group kernel instead
+            const bool ws = use_ws_kernels();
             float* de_scatter = (ws && de_cur) ? const_cast<float*>(de_cur) : nullptr;
-            float* gb2_vertex = (ws && !de_cur) ? G(b.b2) : nullptr;     // the pipelined kernel's block-5 variant takes db2 from here
+            float* gb2_vertex = nullptr;
             RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
                                    gb2_vertex, st));
             RC((ws ? launch_edge_bwd_ws : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E,
-                                  (l == GCRL_N_BLOCKS - 1) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
+                                  (l == GCRL_N_BLOCKS - 1 && !ws) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
                                   S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
         } else if (E > 0) {
             EdgeBwdArgs a;

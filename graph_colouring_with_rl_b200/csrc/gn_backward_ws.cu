@@ -72,6 +72,7 @@ struct BwdWsArgs {
     const float* m; const float* de;          // e_l, d e_l (L2 prefetch; the tiles themselves move by TMA)
     float* dPi; float* dPj;
     float* gW1; float* gW2; float* gb2;
+    int no_de;                                // block 5: there is no d e_l (dm = ca + cb e_l + arg terms, applied here)
     int pf;                                   // L2 prefetch distance in tiles (0 = off)
     int dbg;                                  // timing experiments only (GCRL_WS_DBG): 1 no reds, 2 no gather, 4 no store
     long long* trace;                         // debugging: clock64 per (role, tile, event) of CTA 0, or null
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     const int32_t t0 = tile_t0(i);
                     const uint32_t bytes = (uint32_t)min(TILE, a.E - t0) * 256u;
                     l2_prefetch_bulk(a.m + (int64_t)t0 * 64, bytes);
-                    l2_prefetch_bulk(a.de + (int64_t)t0 * 64, bytes);
+                    if (!a.no_de) l2_prefetch_bulk(a.de + (int64_t)t0 * 64, bytes);
                 }
             };
             for (int i = 1; i < a.pf; ++i) prefetch(i);
@@ -194,11 +195,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                     const int slot = k % WS_NMD, u = k / WS_NMD;
                     mbar_wait(&S.bar_MDempty[slot], (u & 1) ^ 1);
                     WS_TR(true, 2, i, j);
-                    mbar_arrive_expect_tx(&S.bar_MDfull[slot], 16384);
+                    mbar_arrive_expect_tx(&S.bar_MDfull[slot], a.no_de ? 8192 : 16384);
                     tma_load_2d_hint(S.ringMD[slot], &tm_m, 0, t0 + 32 * j, &S.bar_MDfull[slot], pol);
                     tma_load_2d_hint(S.ringMD[slot] + 4096, &tm_m, 32, t0 + 32 * j, &S.bar_MDfull[slot], pol);
-                    tma_load_2d_hint(S.ringMD[slot] + 8192, &tm_de, 0, t0 + 32 * j, &S.bar_MDfull[slot], pol);
-                    tma_load_2d_hint(S.ringMD[slot] + 12288, &tm_de, 32, t0 + 32 * j, &S.bar_MDfull[slot], pol);
+                    if (!a.no_de) {
+                        tma_load_2d_hint(S.ringMD[slot] + 8192, &tm_de, 0, t0 + 32 * j, &S.bar_MDfull[slot], pol);
+                        tma_load_2d_hint(S.ringMD[slot] + 12288, &tm_de, 32, t0 + 32 * j, &S.bar_MDfull[slot], pol);
+                    }
                 }
             }
         }
@@ -454,7 +457,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
             const int c4 = wtid & 15;
             float bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
             int32_t cur_v = -1;
-            float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4;
+            float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4, Gmn = A4, Gmx = A4;
+            int4 Imn = make_int4(-1, -1, -1, -1), Imx = Imn;       // no_de: arg slots / gradients of this thread's 4 columns
             int k = 0;
             for (int i = 0; i < n_cta; ++i) {
               {
@@ -482,11 +486,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                                     cur_v = v;
                                     A4 = __ldg(reinterpret_cast<const float4*>(a.ca + (int64_t)v * 64) + c4);
                                     B4 = __ldg(reinterpret_cast<const float4*>(a.cb + (int64_t)v * 64) + c4);
+                                    if (a.no_de) {
+                                        Imn = __ldg(reinterpret_cast<const int4*>(a.amin + (int64_t)v * 64) + c4);
+                                        Imx = __ldg(reinterpret_cast<const int4*>(a.amax + (int64_t)v * 64) + c4);
+                                        Gmn = __ldg(reinterpret_cast<const float4*>(a.dagg + (int64_t)v * 256 + 64) + c4);
+                                        Gmx = __ldg(reinterpret_cast<const float4*>(a.dagg + (int64_t)v * 256 + 128) + c4);
+                                    }
                                 }
                                 const float4 m4 = *reinterpret_cast<const float4*>(mbox + sw_off<32>(r, c4));
-                                const float4 d4 = *reinterpret_cast<const float4*>(dbox + sw_off<32>(r, c4));
+                                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (!a.no_de) d4 = *reinterpret_cast<const float4*>(dbox + sw_off<32>(r, c4));
                                 r4.x = fmaf(B4.x, m4.x, A4.x) + d4.x; r4.y = fmaf(B4.y, m4.y, A4.y) + d4.y;
                                 r4.z = fmaf(B4.z, m4.z, A4.z) + d4.z; r4.w = fmaf(B4.w, m4.w, A4.w) + d4.w;
+                                if (a.no_de) {
+                                    const int32_t slot_e = t0 + R;
+                                    if (Imn.x == slot_e) r4.x += Gmn.x;
+                                    if (Imn.y == slot_e) r4.y += Gmn.y;
+                                    if (Imn.z == slot_e) r4.z += Gmn.z;
+                                    if (Imn.w == slot_e) r4.w += Gmn.w;
+                                    if (Imx.x == slot_e) r4.x += Gmx.x;
+                                    if (Imx.y == slot_e) r4.y += Gmx.y;
+                                    if (Imx.z == slot_e) r4.z += Gmx.z;
+                                    if (Imx.w == slot_e) r4.w += Gmx.w;
+                                }
                             }
                             bs0 += r4.x; bs1 += r4.y; bs2 += r4.z; bs3 += r4.w;
                             uint2 h, l;
@@ -795,13 +817,14 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st) {
     (void)seg_off;
     if (E == 0) return GCRL_OK;
-    const bool last = (m == nullptr);
+    const bool last = (m == nullptr);          // recompute flavour (unused by the default dispatch)
+    const bool no_de = (m != nullptr && de == nullptr);
     BwdWsArgs a;
     a.Pi = Pi; a.Pj = Pj; a.e_prev = e_prev; a.De = De;
     a.W1 = W1; a.ldW1 = ldW1; a.coff = coff; a.W2 = W2; a.b2 = b2;
     a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
-    a.m = m; a.de = de; a.trace = nullptr;
+    a.m = m; a.de = de; a.trace = nullptr; a.no_de = no_de ? 1 : 0;
     {
         static int pf = -1;
         if (pf < 0) { const char* e = getenv("GCRL_WS_PF"); pf = e ? atoi(e) : 1; }
@@ -816,12 +839,12 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
     // unused maps point at a valid [N,64] array so that encoding never fails
     if ((rc = make_tmap_rows64(&te, first ? Pi : e_prev, first ? N : E, 32))) return rc;
     if ((rc = make_tmap_rows64(&tm, last ? Pi : m, last ? N : E, 32))) return rc;
-    if ((rc = make_tmap_rows64(&tde, last ? Pi : de, last ? N : E, 32))) return rc;
+    if ((rc = make_tmap_rows64(&tde, (last || no_de) ? Pi : de, (last || no_de) ? N : E, 32))) return rc;
     if ((rc = make_tmap_rows64(&tout, first ? Pi : de_prev, first ? N : E, 128))) return rc;
     int64_t tiles = (E + TILE - 1) / TILE;
     const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
     int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
-    const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (last ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
+    const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : ((last || no_de) ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
     if (first) rc = x3 ? launch_ws_variant<true, false, true>(te, tm, tde, tout, a, (int)grid, st)
                        : launch_ws_variant<true, false, false>(te, tm, tde, tout, a, (int)grid, st);
     else if (last) rc = x3 ? launch_ws_variant<false, true, true>(te, tm, tde, tout, a, (int)grid, st)

@@ -33,7 +33,8 @@ __device__ __forceinline__ void gemm64(const float (*A)[LDT], const float (*W)[6
 
 // Activations the backward pass needs (one carve of the caller's stash buffer).
 struct Stash {
-    float* e[4];                    // e_1..e_4 [E,64]  (e_5 is never materialised)
+    float* e[5];                    // e_1..e_5 [E,64]  (e_5 only in the tensor-core modes: its backward then runs as a
+                                    // regular pipelined block instead of recomputing it; the network itself discards e_5)
     float* h[GCRL_N_BLOCKS];        // h_1..h_5 [N,64]
     float* Pi[GCRL_N_BLOCKS];       // A_l h_{l-1} + b1_l [N,64]
     float* Pj[GCRL_N_BLOCKS];       // B_l h_{l-1}        [N,64]
@@ -48,7 +49,7 @@ struct Stash {
 
 inline size_t stash_bytes(int64_t N, int64_t E) {
     const size_t n64 = align_up((size_t)N * 64 * 4);
-    size_t b = 4 * align_up((size_t)E * 64 * 4);
+    size_t b = 5 * align_up((size_t)E * 64 * 4);
     b += GCRL_N_BLOCKS * (7 * n64 + align_up((size_t)N * 256 * 4));
     b += 2 * n64;
     return b + 256;
@@ -57,7 +58,7 @@ inline size_t stash_bytes(int64_t N, int64_t E) {
 inline Stash carve_stash(void* p, int64_t N, int64_t E) {
     Arena ar(p, (size_t)-1);
     Stash s;
-    for (int i = 0; i < 4; ++i) s.e[i] = ar.take<float>((size_t)E * 64);
+    for (int i = 0; i < 5; ++i) s.e[i] = ar.take<float>((size_t)E * 64);
     for (int i = 0; i < GCRL_N_BLOCKS; ++i) {
         s.h[i] = ar.take<float>((size_t)N * 64);
         s.Pi[i] = ar.take<float>((size_t)N * 64);

@@ -538,7 +538,8 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
     const float* h_prev = x;
     for (int l = 0; l < GCRL_N_BLOCKS; ++l) {
         const bool last = (l == GCRL_N_BLOCKS - 1);
-        float* e_out = last ? nullptr : (stash_p ? S.e[l] : eb[l & 1]);
+        const bool keep_e5 = stash_p && math_mode != GCRL_MATH_FP32 && use_ws_kernels();
+        float* e_out = last ? (keep_e5 ? S.e[l] : nullptr) : (stash_p ? S.e[l] : eb[l & 1]);
         float* agg = stash_p ? S.agg[l] : aggb;
         float* hl = stash_p ? S.h[l] : hb[l & 1];
         rc = launch_edge_fwd_mode(math_mode, net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
