@@ -529,6 +529,11 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
 // GCRL_EDGE_IMPL=tc selects the older single-group tensor-core kernels (A/B comparisons)
 bool use_ws_kernels();
+// gn_node_tc.cu: vertex-side products on the tensor cores
+int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
+               int accumulate, int64_t N, cudaStream_t st);
+int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
+               int gcol0, int64_t N, cudaStream_t st);
 
 
 }  // namespace gcrl
@@ -624,7 +629,20 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         const float* h_prev = (l == 0) ? x : S.h[l - 1];
         const int ldU1 = 256 + b.Dv;
         const int ldW1 = 2 * b.Dv + b.De;
-        // update MLP (architecture.py:68-78)
+        // update MLP (architecture.py:68-78); tensor-core math modes run the 64-wide products on tcgen05 (gn_node_tc.cu)
+        static const bool node_ffma = getenv("GCRL_NODE_IMPL") && getenv("GCRL_NODE_IMPL")[0] == 'f';
+        const bool vtc = math_mode != GCRL_MATH_FP32 && !node_ffma;
+        const bool x3 = math_mode == GCRL_MATH_BF16X3;
+        if (vtc) {
+            RC(wgrad64_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, N, st));
+            RC(colsum(dh, N, 64, G(b.c2), st));
+            RC(dgrad64_tc(x3, dh, b.U2, 64, 0, du1, 64, 0, S.u1[l], 0, N, st));
+            RC(wgrad64_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, b.Dv == 64 ? 1 : 0, G(b.U1), ldU1, 0, N, st));
+            if (b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
+            RC(colsum(du1, N, 64, G(b.c1), st));
+            for (int c = 0; c < 4; ++c) RC(dgrad64_tc(x3, du1, b.U1, ldU1, 64 * c, dagg, 256, 64 * c, nullptr, 0, N, st));
+            if (l > 0) RC(dgrad64_tc(x3, du1, b.U1, ldU1, 256, dh_prev, 64, 0, nullptr, 0, N, st));
+        } else {
         RC(wgrad(dh, 64, 64, S.u1[l], 64, 64, G(b.U2), 64, 0, N, st));
         RC(colsum(dh, N, 64, G(b.c2), st));
         RC(dgrad(dh, 64, 64, b.U2, 64, 0, 64, du1, 64, S.u1[l], 0, N, st));
@@ -633,6 +651,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         RC(colsum(du1, N, 64, G(b.c1), st));
         RC(dgrad(du1, 64, 64, b.U1, ldU1, 0, 256, dagg, 256, nullptr, 0, N, st));
         if (l > 0) RC(dgrad(du1, 64, 64, b.U1, ldU1, 256, 64, dh_prev, 64, nullptr, 0, N, st));
+        }
         // message MLP + aggregation (architecture.py:51-66)
         GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)N * 64 * 4, st));
         GCRL_CUDA(cudaMemsetAsync(dPj, 0, (size_t)N * 64 * 4, st));
@@ -670,10 +689,19 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             RC(launch_edge_bwd(a, l == 0, st));
         }
         // vertex columns of message_mlp.0: Pi = A h + b1, Pj = B h
-        RC(wgrad(dPi, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, 0, N, st));
-        RC(wgrad(dPj, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, b.Dv, N, st));
+        if (vtc && b.Dv == 64) {
+            RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, N, st));
+            RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, N, st));
+        } else {
+            RC(wgrad(dPi, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, 0, N, st));
+            RC(wgrad(dPj, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, b.Dv, N, st));
+        }
         RC(colsum(dPi, N, 64, G(b.b1), st));
-        if (l > 0) {
+        if (l > 0 && vtc) {
+            RC(dgrad64_tc(x3, dPi, b.W1, ldW1, 0, dh_prev, 64, 0, nullptr, 1, N, st));
+            RC(dgrad64_tc(x3, dPj, b.W1, ldW1, 64, dh_prev, 64, 0, nullptr, 1, N, st));
+            float* t = dh; dh = dh_prev; dh_prev = t;
+        } else if (l > 0) {
             RC(dgrad(dPi, 64, 64, b.W1, ldW1, 0, 64, dh_prev, 64, nullptr, 1, N, st));
             RC(dgrad(dPj, 64, 64, b.W1, ldW1, 64, 64, dh_prev, 64, nullptr, 1, N, st));
             float* t = dh; dh = dh_prev; dh_prev = t;

@@ -25,8 +25,31 @@ struct RowsGemmArgs {
     int n1, n2;                            // 64-column chunks taken from tensor map 1 / tensor map 2
     const float* xt; int Dt;               // tail: out0[:, o] += sum_{d < Dt} Wt[o * ldWt + colt + d] * xt[row * Dt + d]
     const float* Wt; int ldWt, colt;
+    int wT;                                // weights read transposed: element (o, k) = W[k * ldW + col + o]   (dgrad: dX = dY W)
+    int ocol0, ocol1;                      // column offsets of the two outputs inside their [N, ld] matrices
+    const float* mask; int ldmask;         // out0[r][o] *= (mask[r * ldmask + o] > 0)   (relu' of a stashed activation) or null
+    int accumulate;                        // outputs are added to memory (TMA reduce-add) instead of stored
     int64_t N;
 };
+
+// transposed flavour of load_weight_tile: tile row o (output), column k (contraction) <- W[(k) * ld + col0 + o]
+__device__ __forceinline__ void load_weight_tile_T(const float* W, int ld, int col0, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                   int tid, int nthreads) {
+    for (int t = tid; t < 64 * 8; t += nthreads) {
+        const int o = t & 63, cb = t >> 6;          // consecutive threads read consecutive addresses
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = W[(8 * cb + j) * ld + col0 + o];
+        uint4 h, l;
+        split8(x, h, l);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(hi) + bf_off(o, cb)) = h;
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(lo) + bf_off(o, cb)) = l;
+    }
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
 
 constexpr int NODE_MAX_CHUNKS = 5;
 
@@ -63,8 +86,13 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
     for (int c = 0; c < nch; ++c) {
         __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH);
         __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH + WCH / 2);
-        load_weight_tile(a.W0, a.ldW0, a.col0 + 64 * c, hi, lo, tid, 256);
-        if (NOUT == 128) load_weight_tile(a.W1, a.ldW1, a.col1 + 64 * c, hi + 64 * 64, lo + 64 * 64, tid, 256);
+        if (a.wT) {          // (single K chunk: the contraction runs over the 64 rows of W)
+            load_weight_tile_T(a.W0, a.ldW0, a.col0, hi, lo, tid, 256);
+            if (NOUT == 128) load_weight_tile_T(a.W1, a.ldW1, a.col1, hi + 64 * 64, lo + 64 * 64, tid, 256);
+        } else {
+            load_weight_tile(a.W0, a.ldW0, a.col0 + 64 * c, hi, lo, tid, 256);
+            if (NOUT == 128) load_weight_tile(a.W1, a.ldW1, a.col1 + 64 * c, hi + 64 * 64, lo + 64 * 64, tid, 256);
+        }
     }
     if (tid < 128) bias_s[tid] = tid < 64 ? (a.bias0 ? a.bias0[tid] : 0.f) : ((NOUT == 128 && a.bias1) ? a.bias1[tid - 64] : 0.f);
     for (int t = tid; t < 64 * 8; t += 256) {
@@ -143,6 +171,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
 #pragma unroll
                         for (int d = 0; d < 8; ++d) x = fmaf(wt_s[o * 8 + d], xt[d], x);
                     }
+                    if (a.mask && o < 64) x = (valid && a.mask[(int64_t)(v0 + row) * a.ldmask + o] > 0.f) ? x : 0.f;
                     v[j] = a.relu ? fmaxf(x, 0.f) : x;
                 }
                 *reinterpret_cast<float4*>(l_ptr(Lout, row, (lc0 >> 2) + c)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -152,11 +181,20 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
-            tma_store_2d(&tmo0, 0, v0, L0);             // rows past N are clipped by the tensor map
-            tma_store_2d(&tmo0, 32, v0, L0 + 128 * 32);
-            if (NOUT == 128) {
-                tma_store_2d(&tmo1, 0, v0, L1);
-                tma_store_2d(&tmo1, 32, v0, L1 + 128 * 32);
+            if (a.accumulate) {                          // rows past N are clipped by the tensor map
+                tma_reduce_add_2d(&tmo0, a.ocol0, v0, L0);
+                tma_reduce_add_2d(&tmo0, a.ocol0 + 32, v0, L0 + 128 * 32);
+                if (NOUT == 128) {
+                    tma_reduce_add_2d(&tmo1, a.ocol1, v0, L1);
+                    tma_reduce_add_2d(&tmo1, a.ocol1 + 32, v0, L1 + 128 * 32);
+                }
+            } else {
+                tma_store_2d(&tmo0, a.ocol0, v0, L0);
+                tma_store_2d(&tmo0, a.ocol0 + 32, v0, L0 + 128 * 32);
+                if (NOUT == 128) {
+                    tma_store_2d(&tmo1, a.ocol1, v0, L1);
+                    tma_store_2d(&tmo1, a.ocol1 + 32, v0, L1 + 128 * 32);
+                }
             }
             bulk_commit();
             bulk_wait_read0();
@@ -222,6 +260,107 @@ static int make_tmap_rows(CUtensorMap* out, const float* basep, int64_t rows, in
     return GCRL_OK;
 }
 
+// G[o][gcol0 + 64 c + k] += sum_r Y[r][o] X_c[r][k]: weight gradients of the vertex-side Linear layers.  Y [N,64] and the
+// 64-column chunks X_c of up to two [N, 64 n] matrices arrive by TMA; both become bf16 hi/lo operand tiles that are
+// read MN-major (the contraction runs over the 128 rows of a tile); one TMEM accumulator per chunk lives for the
+// whole kernel and is flushed with one atomic pass per CTA.
+struct RowsWgradArgs {
+    int n1, n2;
+    float* G; int ldG, gcol0;
+    int64_t N;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant__ CUtensorMap tmY,
+                                                         const __grid_constant__ CUtensorMap tm1,
+                                                         const __grid_constant__ CUtensorMap tm2, const RowsWgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* L0 = reinterpret_cast<float*>(base);
+    float* L1 = L0 + 128 * 64;
+    unsigned char* Yop = reinterpret_cast<unsigned char*>(L1 + 128 * 64);
+    unsigned char* Xop = Yop + 32768;
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Xop + 32768);      // [2]
+    uint64_t* bar_mma = bar_tma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 3);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nch = a.n1 + a.n2;
+    if (tid == 0) {
+        mbar_init(&bar_tma[0], 1);
+        mbar_init(&bar_tma[1], 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t id_rows = make_idesc_bf16(64, 64, true, true);
+    uint32_t ph_tma[2] = {0u, 0u}, ph_mma = 0u;
+    // loads are numbered per tile: 0 = Y, 1 + c = X chunk c; load j lands in buffer j & 1
+    auto issue_load = [&](int j, int32_t v0) {
+        float* L = (j & 1) ? L1 : L0;
+        const int c = j - 1;
+        const CUtensorMap* tm = j == 0 ? &tmY : (c < a.n1 ? &tm1 : &tm2);
+        const int col = j == 0 ? 0 : 64 * (c < a.n1 ? c : c - a.n1);
+        mbar_arrive_expect_tx(&bar_tma[j & 1], 128 * 64 * 4);
+        tma_load_2d(L, tm, col, v0, &bar_tma[j & 1]);
+        tma_load_2d(L + 128 * 32, tm, col + 32, v0, &bar_tma[j & 1]);
+    };
+    const int64_t n_tiles = (a.N + 127) / 128;
+    bool first_tile = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int32_t v0 = (int32_t)(tile * 128);
+        if (tid == 0) { issue_load(0, v0); issue_load(1, v0); }
+        for (int j = 0; j <= nch; ++j) {
+            const float* L = (j & 1) ? L1 : L0;
+            mbar_wait(&bar_tma[j & 1], ph_tma[j & 1]);
+            ph_tma[j & 1] ^= 1u;
+            if (j >= 2) {                                 // the previous chunk's MMA has read Xop
+                mbar_wait(bar_mma, ph_mma);
+                ph_mma ^= 1u;
+            }
+            unsigned char* dstop = j == 0 ? Yop : Xop;
+            convert_tile128<X3>(L, reinterpret_cast<__nv_bfloat16*>(dstop), reinterpret_cast<__nv_bfloat16*>(dstop + 16384), tid);
+            fence_proxy_async();
+            __syncthreads();
+            if (warp == 0 && elect_one()) {
+                if (j + 2 <= nch) issue_load(j + 2, v0);
+                if (j >= 1) {
+                    tc_fence_after();
+                    issue_gemm_rows<X3>(tmem + 64 * (j - 1), smem_u32(Yop), smem_u32(Yop) + 16384, smem_u32(Xop), smem_u32(Xop) + 16384,
+                                        id_rows, 128, !first_tile);
+                    umma_commit(bar_mma);
+                }
+            }
+        }
+        mbar_wait(bar_mma, ph_mma);                       // all products of this tile are done: Yop / Xop are free
+        ph_mma ^= 1u;
+        first_tile = false;
+    }
+    if (!first_tile) {
+        tc_fence_after();
+        if (warp < 4) {
+            const int o = 16 * warp + lane;               // accumulator row of an M = 64 product
+            const uint32_t lane_addr = (uint32_t)(32 * warp) << 16;
+            for (int c = 0; c < nch; ++c) {
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[32];
+                    tmem_ld32(tmem + 64 * c + lane_addr + 32 * hh, v);
+                    if (lane < 16)
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) atomicAdd(&a.G[o * a.ldG + a.gcol0 + 64 * c + 32 * hh + jj], v[jj]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // agg rows of vertices without incoming edges take the scatter defaults (0, 0, 0, sqrt(eps)): the edge kernel never
 // visits them (principal_neighbourhood_aggregation.py:45-64 on an empty segment)
 __global__ void k_fix_empty_agg(float* __restrict__ agg, const int32_t* __restrict__ seg_off, int64_t N) {
@@ -279,7 +418,7 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
     a.bias0 = b.c1; a.bias1 = nullptr; a.relu = 1;
     a.n1 = 4; a.n2 = wide_h ? 1 : 0;
     a.xt = wide_h ? nullptr : h_in; a.Dt = wide_h ? 0 : b.Dv; a.Wt = b.U1; a.ldWt = K1; a.colt = 256;
-    a.N = N;
+    a.N = N; a.wT = 0; a.ocol0 = 0; a.ocol1 = 0; a.mask = nullptr; a.ldmask = 0; a.accumulate = 0;
     rc = x3 ? launch_rows_gemm<64, true>(t_agg, t_h, t_u1, t_u1, a, st) : launch_rows_gemm<64, false>(t_agg, t_h, t_u1, t_u1, a, st);
     if (rc) return rc;
     // update_mlp.2
@@ -313,6 +452,51 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
         k_head_dot<<<(int)blocks, 256, 0, st>>>(y2_buf, net.head.F3, net.head.f3, N, q);
         GCRL_LAUNCH_CHECK();
     }
+    return GCRL_OK;
+}
+
+
+// dX[N, 64] (+)= (dY[N,64] . W[64, wcol : wcol + 64]) * (mask > 0), on the tensor cores.  dX may be a 64-column window
+// (column xcol) of a wider matrix [N, ldx].
+int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
+               int accumulate, int64_t N, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    CUtensorMap ty, tx;
+    int rc;
+    if ((rc = make_tmap_rows(&ty, dY, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&tx, dX, N, ldx))) return rc;
+    RowsGemmArgs a;
+    a.W0 = W; a.ldW0 = ldw; a.col0 = wcol; a.W1 = nullptr; a.ldW1 = 0; a.col1 = 0;
+    a.bias0 = nullptr; a.bias1 = nullptr; a.relu = 0; a.n1 = 1; a.n2 = 0;
+    a.xt = nullptr; a.Dt = 0; a.Wt = nullptr; a.ldWt = 0; a.colt = 0;
+    a.wT = 1; a.ocol0 = xcol; a.ocol1 = 0; a.mask = mask; a.ldmask = 64; a.accumulate = accumulate; a.N = N;
+    return x3 ? launch_rows_gemm<64, true>(ty, ty, tx, tx, a, st) : launch_rows_gemm<64, false>(ty, ty, tx, tx, a, st);
+}
+
+// G[o][gcol0 + k] += sum_r Y[r][o] X[r][k] for X = [X1 (64 n1 columns) | X2 (64 n2 columns)]
+int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
+               int gcol0, int64_t N, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    CUtensorMap ty, t1, t2;
+    int rc;
+    if ((rc = make_tmap_rows(&ty, Y, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&t1, X1, N, ld1))) return rc;
+    if ((rc = make_tmap_rows(&t2, n2 ? X2 : X1, N, n2 ? ld2 : ld1))) return rc;
+    RowsWgradArgs a;
+    a.n1 = n1; a.n2 = n2; a.G = G; a.ldG = ldG; a.gcol0 = gcol0; a.N = N;
+    const int smem = 2 * 32768 + 2 * 32768 + 64 + 1024;
+    static bool done = false;
+    if (!done) {
+        GCRL_CUDA(cudaFuncSetAttribute(k_rows_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GCRL_CUDA(cudaFuncSetAttribute(k_rows_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        done = true;
+    }
+    int64_t tiles = (N + 127) / 128;
+    int64_t grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    if (x3) k_rows_wgrad_tc<true><<<(int)grid, 256, smem, st>>>(ty, t1, t2, a);
+    else k_rows_wgrad_tc<false><<<(int)grid, 256, smem, st>>>(ty, t1, t2, a);
+    GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
 
