@@ -188,15 +188,31 @@ class BatchedColouringEnv(object):
 
     def __init__(self, adjs, device=None):
         """adjs: list of [n,n] 0/1 arrays (or reference target dicts)."""
-        self.device = dev = _device() if device is None else torch.device(device)
+        dev = _device() if device is None else torch.device(device)
         mats = [adjacency_from_target(a) if isinstance(a, dict) else np.ascontiguousarray(a, dtype=np.uint8) for a in adjs]
         ns = np.asarray([m.shape[0] for m in mats], dtype=np.int64)
-        self.n_graphs = len(mats)
+        adj = torch.from_numpy(np.concatenate([m.reshape(-1) for m in mats])).to(dev)
+        adj_off = torch.from_numpy(np.concatenate([[0], np.cumsum(ns * ns)[:-1]]).astype(np.int64)).to(dev)
+        self._setup(ns, adj, adj_off, dev)
+
+    @classmethod
+    def from_pool(cls, pool, graph_ids):
+        """Environment batch over graphs that already live on the device (replay.GraphPool): the
+        adjacency bytes are shared with the pool, only the per-graph offsets are built."""
+        self = cls.__new__(cls)
+        ids = np.asarray(graph_ids, dtype=np.int64)
+        adj_off = torch.from_numpy(pool.adj_off_h[ids].copy()).to(pool.device)
+        self._setup(pool.ns[ids], pool.adj, adj_off, pool.device)
+        self.graph_ids = ids
+        return self
+
+    def _setup(self, ns, adj, adj_off, dev):
+        self.device = dev
+        self.n_graphs = int(ns.size)
         self.ns = ns
         self.n_vertices = int(ns.sum())
         self.n_edges = int((ns * (ns - 1)).sum())
-        self.adj = torch.from_numpy(np.concatenate([m.reshape(-1) for m in mats])).to(dev)
-        self.adj_off = torch.from_numpy(np.concatenate([[0], np.cumsum(ns * ns)[:-1]]).astype(np.int64)).to(dev)
+        self.adj, self.adj_off = adj, adj_off
         self.node_off = torch.from_numpy(np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)).to(dev)
         G, N = self.n_graphs, self.n_vertices
         self.colour = torch.empty(N, dtype=torch.int32, device=dev)

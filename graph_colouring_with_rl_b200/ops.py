@@ -284,3 +284,38 @@ def env_first_vertex(adj, adj_off, node_off, n_vertices, want_counts=False):
         check(lib.gcrl_env_first_vertex(ptr(adj), ptr(adj_off), ptr(node_off), G, ptr(action), ptr(counts),
                                         stream_ptr(dev)), 'gcrl_env_first_vertex')
     return (action, counts) if want_counts else action
+
+
+# ---- device replay ring ------------------------------------------------------------------------------
+def replay_store(slot, graph_id, node_off, cur_colour, next_colour, action, reward, done, ring):
+    """ring = (r_graph, r_cur [C,stride] int16, r_next, r_action, r_reward, r_done); slot int32 [n_envs], < 0 skips."""
+    lib = _lib.load()
+    require_cuda(cur_colour, 'cur_colour')
+    dev = cur_colour.device
+    r_graph, r_cur, r_next, r_action, r_reward, r_done = ring
+    with torch.cuda.device(dev):
+        check(lib.gcrl_replay_store(int(slot.numel()), ptr(slot), ptr(graph_id), ptr(node_off), ptr(cur_colour),
+                                    ptr(next_colour), ptr(action), ptr(reward), ptr(done), int(r_cur.shape[1]),
+                                    ptr(r_graph), ptr(r_cur), ptr(r_next), ptr(r_action), ptr(r_reward), ptr(r_done),
+                                    stream_ptr(dev)), 'gcrl_replay_store')
+
+
+def replay_gather(slots, ring, pool_adj, pool_adj_off, pool_n, n_max, out_node_off, out_adj_off, n_vertices,
+                  n_adj_bytes, err=None):
+    """-> (adj uint8 [sum n^2], cur int32 [N], next int32 [N], action int32 [B], reward f32 [B], done int32 [B])."""
+    lib = _lib.load()
+    require_cuda(slots, 'slots')
+    dev = slots.device
+    r_graph, r_cur, r_next, r_action, r_reward, r_done = ring
+    B = int(slots.numel())
+    adj = torch.empty(int(n_adj_bytes), dtype=torch.uint8, device=dev)
+    cur, nxt = _i32(n_vertices, dev), _i32(n_vertices, dev)
+    action, done = _i32(B, dev), _i32(B, dev)
+    reward = torch.empty(B, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.gcrl_replay_gather(B, ptr(slots), ptr(r_graph), ptr(r_cur), ptr(r_next), ptr(r_action),
+                                     ptr(r_reward), ptr(r_done), int(r_cur.shape[1]), ptr(pool_adj),
+                                     ptr(pool_adj_off), ptr(pool_n), int(n_max), ptr(out_node_off),
+                                     ptr(out_adj_off), ptr(adj), ptr(cur), ptr(nxt), ptr(action), ptr(reward),
+                                     ptr(done), ptr(err), stream_ptr(dev)), 'gcrl_replay_gather')
+    return adj, cur, nxt, action, reward, done

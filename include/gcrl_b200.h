@@ -209,6 +209,37 @@ int gcrl_env_first_vertex(const uint8_t* adj, const int64_t* adj_off, const int3
                           int32_t n_graphs, int32_t* action, int32_t* dist_counts,
                           void* stream);
 
+/* ---- device-resident replay ring (dqn_agent.py:8-65 ReplayBuffer.store_transition /
+ * sample_buffer) ---------------------------------------------------------------
+ * Edges are static per graph, so a transition is (graph id, colours before the step, colours
+ * after, action, reward, done).  The ring arrays are caller-owned: r_graph/r_action/r_done
+ * int32 [capacity], r_reward f32 [capacity], r_cur/r_next int16 [capacity, stride] (-1 padded,
+ * stride >= the largest vertex count).  The host chooses slots (ring index = count % capacity,
+ * dqn_agent.py:33) and samples them (np.random.choice with replacement, :48).
+ * store: environment e of a batched env (node_off [n_envs+1]) with slot[e] >= 0 writes its
+ *   transition to that slot; slot[e] < 0 skips it.
+ * gather: minibatch position b takes ring slot slots[b]; the graph's adjacency bytes are copied
+ *   from the pool (pool_adj [sum n^2], pool_adj_off int64 [P], pool_n int32 [P], n_max = largest
+ *   pool_n) to out_adj + out_adj_off[b]; colours are widened to int32 at out_node_off[b]; the
+ *   outputs are exactly the inputs of gcrl_pack_dense / gcrl_gn_forward / gcrl_td_target_loss.
+ *   out_node_off [batch+1] / out_adj_off [batch+1] are computed by the caller from its host
+ *   mirror of the slots' vertex counts; a mismatch with the ring sets *err = b+1 (err may be
+ *   NULL) and copies nothing for that position. */
+int gcrl_replay_store(int32_t n_envs, const int32_t* slot, const int32_t* graph_id,
+                      const int32_t* node_off, const int32_t* cur_colour,
+                      const int32_t* next_colour, const int32_t* action, const float* reward,
+                      const int32_t* done, int32_t stride, int32_t* r_graph, int16_t* r_cur,
+                      int16_t* r_next, int32_t* r_action, float* r_reward, int32_t* r_done,
+                      void* stream);
+int gcrl_replay_gather(int32_t batch, const int32_t* slots, const int32_t* r_graph,
+                       const int16_t* r_cur, const int16_t* r_next, const int32_t* r_action,
+                       const float* r_reward, const int32_t* r_done, int32_t stride,
+                       const uint8_t* pool_adj, const int64_t* pool_adj_off,
+                       const int32_t* pool_n, int32_t n_max, const int32_t* out_node_off,
+                       const int64_t* out_adj_off, uint8_t* out_adj, int32_t* out_cur,
+                       int32_t* out_next, int32_t* out_action, float* out_reward,
+                       int32_t* out_done, int32_t* err, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

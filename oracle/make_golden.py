@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- generate tests/golden/* by running the UNMODIFIED reference
 (/root/reference, imported through oracle/ref_import.py) in this container.
 
-    python -m oracle.make_golden [stage ...]      stages: graphs env train forward learn rollouts
+    python -m oracle.make_golden [stage ...]      stages: graphs env train forward learn rollouts trainloop hostutils
 
 The fixtures are what travels to the GPU box (where /root/reference does not exist); every
 fixture records the script stage and seeds that produced it.
@@ -301,6 +301,136 @@ def stage_rollouts(ref, ds):
         gaps=np.concatenate(gaps), gaps_len=np.asarray([len(g) for g in gaps], dtype=np.int32),
         provenance=np.asarray('oracle/make_golden.py stage_rollouts: reference test_using_learned_policy, parity_weights_GN'))
     print('rollouts: mean colours %.3f in %.0fs' % (np.mean(used), time.time() - t0))
+
+
+def stage_trainloop(ref, ds, episodes=24):
+    """The reference training loop (dqn_main.py:158-199) for a few episodes from the parity weights:
+    per-episode graph index, action sequence (with a flag for NN-chosen actions and their top-2 Q
+    gap), colours used, the loss of every learn() and weight checksums at the end.  batch_size 8
+    (so the 10 x batch gate opens after ~4 episodes) and a 60-episode epsilon schedule."""
+    import gym
+    import torch.nn.functional as F
+    agent = _load_agent(ref, True)
+    agent.batch_size = 8
+    agent.no_episodes = 60
+    random.seed(3)
+    np.random.seed(3)
+    torch.manual_seed(3)
+    env = gym.make('graph-colouring-v0', dataset_graphs=ds.graphs)
+    losses = []
+    orig_mse = F.mse_loss
+
+    def rec_mse(a, b, *args, **kw):
+        out = orig_mse(a, b, *args, **kw)
+        losses.append(float(out))
+        return out
+    ref.dqn_agent.F.mse_loss = rec_mse
+    seen = {}
+
+    def hook(mod, inp, out):
+        seen['q'] = out[1].detach().view(-1).numpy().copy()
+    h = agent.gn_behaviour.register_forward_hook(hook)
+    gids, acts, flags, gaps, lens, used, scores = [], [], [], [], [], [], []
+    t_step, t0 = 0, time.time()
+    for ep in range(1, episodes + 1):
+        gi, target, cur = env.reset()
+        data, gf = env.GenerateData_v1(target, cur)
+        ep_step, done, score = 0, False, 0
+        while not done:
+            if ep_step == 0:
+                v = random.choice(cur['unassigned_vertices'])
+                flags.append(0)
+                gaps.append(np.inf)
+            else:
+                seen.pop('q', None)
+                v = agent.choose_action(data, gf, cur['unassigned_vertices'])
+                if 'q' in seen:
+                    qs = np.sort(seen['q'][cur['unassigned_vertices']])
+                    flags.append(1)
+                    gaps.append(float(qs[-1] - qs[-2]) if len(qs) > 1 else np.inf)
+                else:
+                    flags.append(0)
+                    gaps.append(np.inf)
+            acts.append(int(v))
+            nxt, r, done, info = env.step(v)
+            ndata, ngf = env.GenerateData_v1(target, nxt)
+            if ep_step > 0:
+                agent.remember(data, gf, np.array(nxt['assigned_vertices_onehot']), v, r, ndata, ngf, int(done))
+            if t_step % agent.update_every == 0:
+                agent.learn()
+            t_step += 1
+            data, gf, cur = ndata, ngf, nxt
+            score += r
+            ep_step += 1
+        agent.episode_no += 1
+        gids.append(gi)
+        lens.append(ep_step)
+        used.append(env.current_graph['no_colours_used'])
+        scores.append(score)
+    h.remove()
+    ref.dqn_agent.F.mse_loss = orig_mse
+    sd_b, sd_t = agent.gn_behaviour.state_dict(), agent.gn_target.state_dict()
+    np.savez_compressed(
+        os.path.join(GOLD, 'train_loop.npz'), graph_ids=np.asarray(gids, dtype=np.int32),
+        ep_len=np.asarray(lens, dtype=np.int32), actions=np.asarray(acts, dtype=np.int32),
+        nn_chosen=np.asarray(flags, dtype=np.int8), gaps=np.asarray(gaps, dtype=np.float32),
+        colours_used=np.asarray(used, dtype=np.int32), scores=np.asarray(scores, dtype=np.int32),
+        losses=np.asarray(losses, dtype=np.float64), buffer_size=np.asarray(agent.memory.current_mem_size),
+        behaviour_sum=np.asarray([float(v.double().sum()) for v in sd_b.values()]),
+        behaviour_abs=np.asarray([float(v.double().abs().sum()) for v in sd_b.values()]),
+        target_sum=np.asarray([float(v.double().sum()) for v in sd_t.values()]),
+        target_abs=np.asarray([float(v.double().abs().sum()) for v in sd_t.values()]),
+        provenance=np.asarray('oracle/make_golden.py stage_trainloop: reference dqn_main.py loop, parity_weights_GN, '
+                              'batch_size 8, no_episodes 60, seeds 3, %d episodes' % episodes))
+    print('trainloop: %d episodes, %d steps, %d learns in %.0fs' % (episodes, len(acts), len(losses), time.time() - t0))
+
+
+def stage_hostutils(ref, ds):
+    """Reference host helpers on small inputs: DIMACS reader, queen graphs, networkx conversion and the
+    three stat-file writers (utils.py:58-125,243-323, construct_queen_graph.py)."""
+    import json
+    import tempfile
+    from collections import namedtuple
+    sys.path.insert(0, os.environ.get('GCRL_REFERENCE_ROOT', '/root/reference'))
+    import construct_queen_graph as cq
+    U = ref.utils
+    col = ('c tiny DIMACS file\nc with a self loop, a duplicate and both directions\np edge 7 9\n'
+           'e 1 2\ne 2 1\ne 1 7\ne 3 4\ne 4 5\ne 5 5\ne 6 3\ne 2 6\ne 1 2\n')
+    out = {'dimacs_text': col}
+    with tempfile.TemporaryDirectory() as d:
+        fp = os.path.join(d, 'tiny.col')
+        with open(fp, 'w') as f:
+            f.write(col)
+        n, el, ea, ind, idx = U.import_dimacs_graph(fp)
+        out['dimacs'] = dict(n=n, edge_list=[list(e) for e in el], edge_attr=list(ea),
+                             ind=[[u, v, k] for u, dd in ind.items() for v, k in dd.items()], indices=sorted(idx))
+        g = U.import_dimacs_graph_as_networkx(fp)
+        out['dimacs_nx_edges'] = sorted([sorted(e) for e in g.edges()])
+        queens = []
+        for seed, (n, k) in enumerate([(12, 3), (12, 4), (20, 4), (25, 5), (30, 6), (16, 2)]):
+            random.seed(seed)
+            el, ea, ind, idx = cq.generate_queen_graph(n, k)
+            queens.append(dict(seed=seed, n=n, k=k, edge_list=[list(e) for e in el], edge_attr=list(ea), indices=list(idx),
+                               after=random.random()))
+        out['queens'] = queens
+        verts, edges = ['a', 'b', 'c', 'd', 'e'], [('a', 'c'), ('e', 'b'), ('c', 'd'), ('d', 'a')]
+        el, ea, ind, idx = U.convert_networkx_to_graph(verts, edges)
+        out['convert'] = dict(vertices=verts, edges=[list(e) for e in edges], edge_list=[list(e) for e in el],
+                              edge_attr=list(ea), indices=list(idx),
+                              ind=[[u, v, k] for u, dd in ind.items() for v, k in dd.items()])
+        T = namedtuple("Stats", ["saved_episodes", "episode_rewards", "colours_used"])
+        V = namedtuple("Stats", ["episode_rewards", "colours_used"])
+        tr = T([1, 2, 3], [-7, -5, -6], [7, 5, 6])
+        va = {0: V([-7.0, -5.0], [7.0, 5.0]), 500: V([-6.0, -4.0], [6.0, 4.0])}
+        be = V([-8.25, -6.5], [8.25, 6.5])
+        U.save_training_stats_to_file(tr, os.path.join(d, 't'))
+        U.save_validation_stats_to_file(va, os.path.join(d, 'v'))
+        U.save_benchmark_stats_to_file(be, os.path.join(d, 'b'))
+        out['stat_files'] = {k: open(os.path.join(d, k)).read() for k in 'tvb'}
+    out['provenance'] = 'oracle/make_golden.py stage_hostutils (reference utils.py / construct_queen_graph.py)'
+    with open(os.path.join(GOLD, 'host_utils.json'), 'w') as f:
+        json.dump(out, f)
+    print('hostutils: wrote', os.path.getsize(os.path.join(GOLD, 'host_utils.json')), 'bytes')
 
 
 def main(argv):
