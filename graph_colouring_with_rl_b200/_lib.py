@@ -10,7 +10,8 @@ import re
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, 'libgcrl_b200.so')
+# GCRL_LIB: load a diagnostic build (e.g. a trace build made with GCRL_LIB_OUT + GCRL_NVCC_FLAGS) instead
+LIB_PATH = os.environ.get('GCRL_LIB') or os.path.join(_PKG_DIR, 'libgcrl_b200.so')
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), 'include', 'gcrl_b200.h')
 
 GCRL_MATH_FP32 = 0

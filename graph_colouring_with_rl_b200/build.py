@@ -10,7 +10,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, 'csrc')
-LIB_PATH = os.path.join(PKG_DIR, 'libgcrl_b200.so')
+LIB_PATH = os.environ.get('GCRL_LIB_OUT') or os.path.join(PKG_DIR, 'libgcrl_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
 CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden',
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     """Compile every csrc/*.cu into one shared library.  Returns the library path."""
     if not force and not _stale():
         return LIB_PATH
-    objdir = os.path.join(PKG_DIR, 'build')
+    objdir = os.path.join(PKG_DIR, 'build' if not os.environ.get('GCRL_LIB_OUT') else 'build_diag')
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in sources():

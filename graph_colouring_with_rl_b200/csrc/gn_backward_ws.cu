@@ -74,7 +74,7 @@ struct BwdWsArgs {
     float* gW1; float* gW2; float* gb2;
     int no_de;                                // block 5: there is no d e_l (dm = ca + cb e_l + arg terms, applied here)
     int pf;                                   // L2 prefetch distance in tiles (0 = off)
-    int dbg;                                  // timing experiments only (GCRL_WS_DBG): 1 no reds, 2 no gather, 4 no store
+    int dbg;                                  // timing experiments only (GCRL_WS_DBG): 1 no reds, 2 no gather, 4 no store, 8 single-pass bf16 weight-gradient products
     long long* trace;                         // debugging: clock64 per (role, tile, event) of CTA 0, or null
 };
 
@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 tc_fence_after();
                 WS_TR(lane == 0, 1, i, 1);
                 if (elect_one()) {
-                    issue_gemm_rows<X3, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
+                    if (a.dbg & 8) issue_gemm_rows<false, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
+                    else issue_gemm_rows<X3, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);
                     issue_gemm_featT<X3, true>(t_accA0 + 64 * (i % 3), b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);
                     umma_commit(&S.bar_acc4full[i % 3]);
                 }
@@ -284,7 +285,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
                 tc_fence_after();
                 WS_TR(lane == 0, 1, i, 3);
                 if (elect_one()) {
-                    issue_gemm_rows<X3, true>(t_c, b2_hi, b2_lo, b1_hi, b1_hi + 16384, id_rows, 128, i > 0);
+                    if (a.dbg & 8) issue_gemm_rows<false, true>(t_c, b2_hi, b2_lo, b1_hi, b1_hi + 16384, id_rows, 128, i > 0);
+                    else issue_gemm_rows<X3, true>(t_c, b2_hi, b2_lo, b1_hi, b1_hi + 16384, id_rows, 128, i > 0);
                     if (!FIRST) issue_gemm_featT<X3, true>(t_accB0 + 64 * s, b2_hi, b2_lo, wc_hi, wc_lo, id_featT, false);
                     umma_commit(&S.bar_acc6full[s]);
                     if (FIRST) umma_commit(&S.bar_B1free[s]);

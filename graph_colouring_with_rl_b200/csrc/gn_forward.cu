@@ -418,6 +418,12 @@ int launch_edge_fwd_ws(const BlockW& b, bool first, bool x3, const float* Pi, co
 bool use_ws_kernels();
 bool use_ws_forward();
 
+// gn_forward_wg.cu (four warp groups per SM: the default; GCRL_FWD_IMPL=tc / ws select the other two)
+int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
+                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
+int fwd_impl();
+
 // dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
 int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
                          const float* e_prev, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
@@ -425,8 +431,8 @@ int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float
                          cudaStream_t st) {
     const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
     if (math_mode != GCRL_MATH_FP32 && tc_ok)
-        return (use_ws_forward() ? launch_edge_fwd_ws : launch_edge_fwd_tc)(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out,
-                                  agg, var, amin, amax, st);
+        return (fwd_impl() == 2 ? launch_edge_fwd_ws : fwd_impl() == 1 ? launch_edge_fwd_tc : launch_edge_fwd_wg)(
+            b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
     return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
 }
 

@@ -1,0 +1,343 @@
+// gn_forward_wg.cu -- fused edge kernel of the GN forward pass, four tiles in flight per SM.
+//
+// Same math and fusion as k_edge_fwd_tc (gn_forward_tc.cu; reference: architecture.py:51-66): message MLP on
+// tcgen05 (bf16 / bf16x3 split operands, fp32 accumulate in TMEM), e_l stored by TMA, PNA aggregation fused in.
+// k_edge_fwd_tc runs its phases one after the other in a 256-thread CTA and relies on a second CTA per SM to fill
+// the gaps; its counters say latency: 40 % issue utilisation, a quarter of the stall samples on barriers and
+// another quarter on loads, 16 warps per SM.  Shared memory (110 KB per CTA, 32 KB of it a private copy of the
+// weights) is what stops a third CTA.  This kernel keeps the phase structure but packs FOUR independent 128-thread
+// warp groups into one CTA per SM:
+//   * the weight tiles (32 KB) are shared by the four groups;
+//   * a group owns ONE 32 KB tile buffer T that is, in turn, the TMA landing tile of e_{l-1} (fp32), the bf16 hi/lo
+//     operand tile (converted in place through registers), the hid operand tile and the fp32 staging tile of m_l
+//     (TMA store source + reducer input);
+//   * Pi[dst] + Pj[src] never touch shared memory: they are gathered in the 16x256b TMEM fragment layout and
+//     written with tcgen05.st, G1 accumulates on top (the backward's trick, gn_backward_ws.cu);
+//   * groups synchronise with named barriers and their own mbarriers only, so one group's MMA / TMA / gather
+//     latency is covered by the other three.
+// TMEM: 128 columns per group (acc1, acc2) = all 512.  Shared memory: 32 + 4 x (32 + 12) + ids = 214 KB.
+#define GCRL_MBAR_TIMEOUT   // counted waits: a protocol bug traps instead of hanging the GPU
+#include "gn_common.cuh"
+#include "ws.cuh"
+#include <stdlib.h>
+
+namespace gcrl {
+
+using namespace tc;
+
+constexpr int WG_N = 4;
+constexpr int WG_THREADS = 128 * WG_N;
+
+struct FwdWgSmem {
+    __nv_bfloat16 Wc[2][64 * 64];        // C hi/lo (FIRST: C^T in fp32 [d][o])
+    __nv_bfloat16 W2[2][64 * 64];
+    unsigned char T[WG_N][32768];        // per group: landing fp32 -> operand hi|lo -> hid hi|lo -> m fp32
+    RedScratch red[WG_N];
+    float b2[64];
+    int32_t dst[WG_N][TILE];
+    int32_t src[WG_N][TILE];
+    uint32_t start_bits[WG_N][4];
+    uint64_t bar_tma[WG_N], bar_mma[WG_N];
+    uint32_t tmem_base;
+};
+
+struct FwdWgArgs {
+    const float* Pi; const float* Pj;
+    const float* e_prev; int De;
+    const float* W1; int ldW1, coff;
+    const float* W2; const float* b2;
+    const int32_t* seg_off; const int32_t* src; const int32_t* dst;
+    int32_t N, E;
+    float* m_out;
+    AggOut out;
+};
+
+template <bool FIRST, bool X3, bool ARG>
+__global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_constant__ CUtensorMap tm_in,
+                                                              const __grid_constant__ CUtensorMap tm_out, const FwdWgArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FwdWgSmem& S = *reinterpret_cast<FwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, wg = tid >> 7, lt = tid & 127, w = lt >> 5, lane = tid & 31;
+    const int bar_id = 1 + wg;                     // named barrier of this group (0 is __syncthreads)
+
+    if (tid == 0) {
+        for (int g = 0; g < WG_N; ++g) { mbar_init(&S.bar_tma[g], 1); mbar_init(&S.bar_mma[g], 1); }
+        fence_barrier_init();
+        if (!FIRST) tma_prefetch_desc(&tm_in);
+        if (a.m_out) tma_prefetch_desc(&tm_out);
+    }
+    if (tid < 32) tmem_alloc<512>(&S.tmem_base);
+    load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, WG_THREADS);
+    if (!FIRST) load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, WG_THREADS);
+    float (*Cf)[64] = reinterpret_cast<float (*)[64]>(&S.Wc[0][0]);   // FIRST: C^T in fp32 [d][o]
+    if (FIRST)
+        for (int t = tid; t < a.De * 64; t += WG_THREADS) Cf[t >> 6][t & 63] = a.W1[(t & 63) * a.ldW1 + a.coff + (t >> 6)];
+    if (tid < 64) S.b2[tid] = a.b2[tid];
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t t_acc1 = S.tmem_base + 128 * wg, t_acc2 = t_acc1 + 64;
+    const uint32_t lane_addr = (uint32_t)(32 * w) << 16;
+    const uint32_t idesc = make_idesc_bf16(128, 64, false, false);
+    unsigned char* const T = S.T[wg];
+    float* const M = reinterpret_cast<float*>(T);
+    __nv_bfloat16* const Bh = reinterpret_cast<__nv_bfloat16*>(T);
+    __nv_bfloat16* const Bl = reinterpret_cast<__nv_bfloat16*>(T + 16384);
+    int32_t* const dst_s = S.dst[wg];
+    int32_t* const src_s = S.src[wg];
+    RedScratch* const red = &S.red[wg];
+    uint64_t* const bar_tma = &S.bar_tma[wg];
+    uint64_t* const bar_mma = &S.bar_mma[wg];
+    uint32_t ph_tma = 0, ph_mma = 0;
+    const int cp = 2 * (lane & 3);
+    int32_t cur_d = -1;                            // destination whose Pi row is cached in piv
+    float2 piv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) piv[c] = make_float2(0.f, 0.f);
+
+    const int64_t n_items = ((int64_t)a.E + ITEM_EDGES - 1) / ITEM_EDGES;
+    for (int64_t it = (int64_t)blockIdx.x * WG_N + wg; it < n_items; it += (int64_t)gridDim.x * WG_N) {
+        const int32_t v0 = seg_lower_bound(a.seg_off, a.N, it * ITEM_EDGES);
+        const int32_t v1 = (it + 1 == n_items) ? a.N : seg_lower_bound(a.seg_off, a.N, (it + 1) * ITEM_EDGES);
+        const int32_t e0 = a.seg_off[v0], e1 = a.seg_off[v1];
+        Carry carry;
+        carry.dst = -1;
+        stat_init(carry.s);
+        if (!FIRST && lt == 0 && e0 < e1) {
+            mbar_arrive_expect_tx(bar_tma, 128 * 64 * 4);
+            tma_load_2d(T, &tm_in, 0, e0, bar_tma);
+            tma_load_2d(T + 16384, &tm_in, 32, e0, bar_tma);
+        }
+        int32_t nd = -1, ns = 0;
+        if (e0 + lt < e1) { nd = __ldg(a.dst + e0 + lt); ns = __ldg(a.src + e0 + lt); }
+        for (int32_t t0 = e0; t0 < e1; t0 += TILE) {
+            const int nrows = min(TILE, e1 - t0);
+            dst_s[lt] = nd;
+            src_s[lt] = ns;
+            named_sync(bar_id, 128);
+            {
+                const bool st = lt > 0 && lt < nrows && dst_s[lt] != dst_s[lt - 1];
+                const uint32_t bits = __ballot_sync(0xffffffffu, st);
+                if (lane == 0) S.start_bits[wg][w] = bits;
+                nd = -1; ns = 0;
+                if (t0 + TILE + lt < e1) { nd = __ldg(a.dst + t0 + TILE + lt); ns = __ldg(a.src + t0 + TILE + lt); }
+            }
+            // ---- Pi[dst] + Pj[src] -> acc1 (TMEM), two 16-lane fragment groups per warp ------------------------
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int ra = 32 * w + 16 * g + (lane >> 2), rb = ra + 8;
+                const int32_t da = dst_s[ra], db = dst_s[rb];
+                const bool va = da >= 0, vb = db >= 0;
+                const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)src_s[ra] * 64 + cp);
+                const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)src_s[rb] * 64 + cp);
+                float2 ya[8], yb[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { ya[c] = __ldg(pja + 4 * c); yb[c] = __ldg(pjb + 4 * c); }
+                if (va && da != cur_d) {          // new segment: refresh the cached Pi row
+                    cur_d = da;
+                    const float2* pia = reinterpret_cast<const float2*>(a.Pi + (int64_t)da * 64 + cp);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) piv[c] = __ldg(pia + 4 * c);
+                }
+                const bool b_other = vb && db != cur_d;
+                const float2* pib = reinterpret_cast<const float2*>(a.Pi + (int64_t)(vb ? db : 0) * 64 + cp);
+                float v[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float2 xb = piv[c];
+                    if (b_other) xb = __ldg(pib + 4 * c);
+                    v[4 * c + 0] = va ? piv[c].x + ya[c].x : 0.f;
+                    v[4 * c + 1] = va ? piv[c].y + ya[c].y : 0.f;
+                    v[4 * c + 2] = vb ? xb.x + yb[c].x : 0.f;
+                    v[4 * c + 3] = vb ? xb.y + yb[c].y : 0.f;
+                }
+                if (FIRST) {
+                    // block 1: C e is De FMAs per element, folded in here ((Pi + Pj) + C e)
+                    for (int d = 0; d < a.De; ++d) {
+                        const float ea = va ? a.e_prev[(int64_t)(t0 + ra) * a.De + d] : 0.f;
+                        const float eb = vb ? a.e_prev[(int64_t)(t0 + rb) * a.De + d] : 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float2 cc = *reinterpret_cast<const float2*>(&Cf[d][8 * c + cp]);
+                            v[4 * c + 0] = fmaf(ea, cc.x, v[4 * c + 0]);
+                            v[4 * c + 1] = fmaf(ea, cc.y, v[4 * c + 1]);
+                            v[4 * c + 2] = fmaf(eb, cc.x, v[4 * c + 2]);
+                            v[4 * c + 3] = fmaf(eb, cc.y, v[4 * c + 3]);
+                        }
+                    }
+                }
+                tmem_st_16x256b_x8(t_acc1 + ((uint32_t)(32 * w + 16 * g) << 16), v);
+            }
+            tmem_st_wait();
+            if (!FIRST) {
+                // ---- e_{l-1}: fp32 landing tile -> bf16 hi/lo operand tile, in place through registers ----------
+                mbar_wait(bar_tma, ph_tma);
+                ph_tma ^= 1;
+                float4 x[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int t = k * 128 + lt;
+                    x[k] = *reinterpret_cast<const float4*>(l_ptr(M, t >> 4, t & 15));
+                }
+                named_sync(bar_id, 128);           // every row has been read before any operand row is written
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int t = k * 128 + lt;
+                    const int r = t >> 4, c4 = t & 15;
+                    uint2 h, l;
+                    split4<X3>(x[k], h, l);
+                    const uint32_t off = bf_off(r, c4 >> 1) + (c4 & 1) * 8;
+                    *reinterpret_cast<uint2*>(T + off) = h;
+                    if (X3) *reinterpret_cast<uint2*>(T + 16384 + off) = l;
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_sync(bar_id, 128);
+            tc_fence_after();
+            if (!FIRST) {
+                if (w == 0 && elect_one()) {
+                    issue_gemm_feat<X3>(t_acc1, smem_u32(Bh), smem_u32(Bl), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
+                    umma_commit(bar_mma);
+                }
+                mbar_wait(bar_mma, ph_mma);
+                ph_mma ^= 1;
+                tc_fence_after();
+            }
+            // ---- hid = relu(acc1) -> operand tile (thread = row, two 32-column halves) ----------------------------
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float acc[32];
+                tmem_ld32(t_acc1 + lane_addr + 32 * half, acc);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float y[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) y[j] = fmaxf(acc[8 * c + j], 0.f);
+                    store_split8<X3>(y, Bh, Bl, lt, 4 * half + c);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_sync(bar_id, 128);
+            if (w == 0 && elect_one()) {
+                tc_fence_after();
+                issue_gemm_feat<X3>(t_acc2, smem_u32(Bh), smem_u32(Bl), smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, ph_mma);
+            ph_mma ^= 1;
+            tc_fence_after();
+            // ---- m = acc2 + b2 -> M (fp32 staging over the operand tile: G2 has finished reading it) ---------------
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float acc[32];
+                tmem_ld32(t_acc2 + lane_addr + 32 * half, acc);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&S.b2[32 * half + 4 * c]);
+                    *reinterpret_cast<float4*>(l_ptr(M, lt, 8 * half + c)) =
+                        make_float4(acc[4 * c] + bb.x, acc[4 * c + 1] + bb.y, acc[4 * c + 2] + bb.z, acc[4 * c + 3] + bb.w);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_sync(bar_id, 128);
+            // ---- store e_l + segmented PNA reduction -------------------------------------------------------------------
+            const bool tma_store = a.m_out && nrows == TILE;
+            if (tma_store) {
+                if (lt == 0) {
+                    tma_store_2d(&tm_out, 0, t0, M);
+                    tma_store_2d(&tm_out, 32, t0, M + 128 * 32);
+                    bulk_commit();
+                }
+            } else if (a.m_out) {
+                float4* gp = reinterpret_cast<float4*>(a.m_out + (int64_t)t0 * 64);
+#pragma unroll 4
+                for (int k = 0; k < 16; ++k) {
+                    const int idx = k * 128 + lt;
+                    const int r = idx >> 4, c4 = idx & 15;
+                    if (r < nrows) __stcs(gp + idx, *reinterpret_cast<const float4*>(l_ptr(M, r, c4)));
+                }
+            }
+            tile_reduce_scan_sw_t<ARG>(M, dst_s, S.start_bits[wg], nrows, t0, red, a.out, lt);
+            tile_reduce_scan_sw_t<ARG>(M, dst_s, S.start_bits[wg], nrows, t0, red, a.out, lt + 128);
+            if (tma_store && lt == 0) bulk_wait_read0();
+            fence_proxy_async();                   // generic reads of M are ordered before the next TMA load into it
+            named_sync(bar_id, 128);
+            if (!FIRST && lt == 64 && t0 + TILE < e1) {
+                mbar_arrive_expect_tx(bar_tma, 128 * 64 * 4);
+                tma_load_2d(T, &tm_in, 0, t0 + TILE, bar_tma);
+                tma_load_2d(T + 16384, &tm_in, 32, t0 + TILE, bar_tma);
+            }
+            if (lt < 64) tile_reduce_chain_t(nrows, red, carry, a.out, lt);
+        }
+        if (lt < 64) carry_flush_t(carry, a.out, lt);
+        named_sync(bar_id, 128);   // reducer scratch quiescent before the next item
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc<512>(S.tmem_base);
+}
+
+template <bool FIRST, bool X3, bool ARG>
+static int launch_wg_variant(const CUtensorMap& tin, const CUtensorMap& tout, const FwdWgArgs& a, int grid, cudaStream_t st) {
+    const int smem = (int)sizeof(FwdWgSmem) + 1024;
+    static bool done = false;
+    if (!done) {
+        GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd_wg<FIRST, X3, ARG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        done = true;
+    }
+    k_edge_fwd_wg<FIRST, X3, ARG><<<grid, WG_THREADS, smem, st>>>(tin, tout, a);
+    return GCRL_OK;
+}
+
+// GCRL_FWD_IMPL: "wg" (default) this kernel, "tc" the single-group kernel with two CTAs per SM, "ws" the
+// warp-specialised pipeline
+int fwd_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GCRL_FWD_IMPL");
+        v = 0;
+        if (e && e[0] == 't' && e[1] == 'c') v = 1;
+        if (e && e[0] == 'w' && e[1] == 's') v = 2;
+    }
+    return v;
+}
+
+// Tensor-core edge forward, four warp groups per SM; same contract as launch_edge_fwd_tc (gn_forward_tc.cu).
+int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
+                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st) {
+    if (E == 0) return GCRL_OK;
+    FwdWgArgs a;
+    a.Pi = Pi; a.Pj = Pj; a.e_prev = e_prev; a.De = b.De;
+    a.W1 = b.W1; a.ldW1 = 2 * b.Dv + b.De; a.coff = 2 * b.Dv;
+    a.W2 = b.W2; a.b2 = b.b2;
+    a.seg_off = seg_off; a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
+    a.m_out = m_out;
+    a.out.agg = agg; a.out.var = var; a.out.amin = amin; a.out.amax = amax; a.out.seg_off = seg_off;
+    CUtensorMap tin, tout;
+    int rc = make_tmap_rows64(&tin, first ? Pi : e_prev, first ? N : E, 128);   // FIRST never dereferences tin
+    if (rc) return rc;
+    rc = make_tmap_rows64(&tout, m_out ? m_out : Pi, m_out ? E : N, 128);
+    if (rc) return rc;
+    const int64_t items = (E + ITEM_EDGES - 1) / ITEM_EDGES;
+    int64_t grid = sm_count();
+    if (grid > (items + WG_N - 1) / WG_N) grid = (items + WG_N - 1) / WG_N;
+    const int tok = prof_begin(first ? GCRL_PROF_EDGE_FWD_FIRST : (m_out ? GCRL_PROF_EDGE_FWD : GCRL_PROF_EDGE_FWD_LAST), st);
+    const bool want_arg = amin != nullptr;
+#define WG_LAUNCH(F, X, W) rc = launch_wg_variant<F, X, W>(tin, tout, a, (int)grid, st)
+    if (first) { if (x3) { if (want_arg) WG_LAUNCH(true, true, true); else WG_LAUNCH(true, true, false); }
+                 else    { if (want_arg) WG_LAUNCH(true, false, true); else WG_LAUNCH(true, false, false); } }
+    else       { if (x3) { if (want_arg) WG_LAUNCH(false, true, true); else WG_LAUNCH(false, true, false); }
+                 else    { if (want_arg) WG_LAUNCH(false, false, true); else WG_LAUNCH(false, false, false); } }
+#undef WG_LAUNCH
+    prof_end(tok, st);
+    if (rc) return rc;
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+}  // namespace gcrl
