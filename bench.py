@@ -291,7 +291,7 @@ def main():
     dom = max((k for k in kernels if k in bytes_per_edge), key=lambda k: kernels[k]['share_of_step'])
     # which kernel serves each launch kind (gn_forward.cu / gn_backward.cu dispatch): the pipelined backward
     # (k_edge_bwd_ws) for blocks 1-4, the single-group tensor-core kernels elsewhere
-    fwd_impl = '_ws' if os.environ.get('GCRL_FWD_IMPL', '') == 'ws' else '_tc'
+    fwd_impl = {'ws': '_ws', 'tc': '_tc'}.get(os.environ.get('GCRL_FWD_IMPL', '')[:2], '_wg')
     bwd_impl = '_tc' if os.environ.get('GCRL_EDGE_IMPL', '') == 'tc' else '_ws'
     if args.math == 'fp32':
         fwd_impl = bwd_impl = ''
@@ -342,6 +342,7 @@ def main():
         line_roll = bench_rollouts(agent, dev, args, rank, world, max_over_ranks, barrier)
         if rank == 0:
             line['rollouts'] = line_roll
+            line['train_loop'] = bench_train_loop(dev, args)
             v, cores, times = oracle_fwd_bwd_graphs_per_sec(n, args.cpu_sample_graphs, 3)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d ER(0.5) graphs x %d vertices, oracle/gn_oracle.py fwd+bwd (reference op order, '
@@ -351,6 +352,36 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_train_loop(dev, args):
+    """The device training loop (dqn_main.DeviceTrainer, reference dqn_main.py:158-199) on the shapes of
+    BASELINE.json configs[1]: graphs of 15-50 vertices, minibatch 64, learn every 5 environment steps, 64 episodes
+    in lock step, everything per-step on the device (replay ring included)."""
+    import contextlib
+    import numpy as np
+    import torch
+    from graph_colouring_with_rl_b200.dqn_agent import DQNAgentGN
+    from graph_colouring_with_rl_b200.dqn_main import DeviceTrainer
+    from graph_colouring_with_rl_b200.utils import erdos_renyi_adjacency
+    rng = np.random.default_rng(0)
+    graphs = [erdos_renyi_adjacency(int(n), 0.5, rng) for n in rng.integers(15, 51, size=256)]
+    torch.manual_seed(0)
+    agent = DQNAgentGN(2, 1, 0, math_mode=args.math)
+    n_envs, warm, timed_eps = 64, 128, 512
+    with contextlib.redirect_stdout(sys.stderr):          # the agent prints 'Starting learning' like the reference
+        tr = DeviceTrainer(agent, graphs, None, n_envs=n_envs, device_seed=0)
+        tr.run(warm, verbose=False)                       # fills the ring past the 10 x batch gate
+        torch.cuda.synchronize()
+        t0, s0, l0 = time.perf_counter(), tr.t_step, len(tr.losses)
+        tr.run(warm + timed_eps, verbose=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {'workload': '256 ER(0.5) graphs of 15-50 vertices, %d episodes in lock step, minibatch %d, learn every %d env steps, '
+                        '%d timed episodes after %d warm-up' % (n_envs, agent.batch_size, agent.update_every, timed_eps, warm),
+            'episodes_per_sec': timed_eps / dt, 'env_steps_per_sec': (tr.t_step - s0) / dt,
+            'learn_steps_per_sec': (len(tr.losses) - l0) / dt, 'replay_ring_bytes': tr.memory.bytes(),
+            'timing': 'host wall clock around the loop (it synchronises once per environment step)'}
 
 
 def bench_learn_step(learner, batch, timed, args, G, world):

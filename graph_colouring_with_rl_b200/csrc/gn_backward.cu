@@ -529,6 +529,13 @@ int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, co
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
 // GCRL_EDGE_IMPL=tc selects the older single-group tensor-core kernels (A/B comparisons)
 bool use_ws_kernels();
+// gn_backward_wg.cu (two independent tile chains per SM; default.  GCRL_EDGE_IMPL=ws selects the pipeline above)
+int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
+                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
+                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
+                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
+int bwd_impl();
 // gn_node_tc.cu: vertex-side products on the tensor cores
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
                int accumulate, int64_t N, cudaStream_t st);
@@ -668,7 +675,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             float* gb2_vertex = nullptr;
             RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
                                    gb2_vertex, st));
-            RC((ws ? launch_edge_bwd_ws : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
+            RC((ws ? (bwd_impl() == 0 ? launch_edge_bwd_wg : launch_edge_bwd_ws) : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E,
                                   (l == GCRL_N_BLOCKS - 1 && !ws) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
                                   S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));

@@ -1,0 +1,502 @@
+// gn_backward_wg.cu -- fused edge kernel of the GN backward pass, two independent tile chains per SM.
+//
+// Same math as k_edge_bwd_ws (gn_backward_ws.cu; reference: loss.backward() through architecture.py:51-66,
+// dqn_agent.py:219).  That kernel is a warp-specialised pipeline whose stages hand ONE tile chain
+//   ep1 (hid) -> G3/G4 -> ep3 (dz1) -> G5/G6
+// from role to role; shared memory (224 KB) leaves no room to double-buffer hid/dz1 and dm, so consecutive tiles'
+// chains cannot overlap and the kernel's time is the chain's latency (5.4 ms of its 8.0 ms per launch with every
+// memory side effect switched off; dropping 32 of its 84 UMMAs per tile changes the time by 1 %).
+// The forward showed the cheaper cure for a latency-bound chain (gn_forward_wg.cu): more independent chains per SM
+// instead of more stages per chain.  Here: TWO 256-thread groups per CTA (one CTA per SM), each walking its own
+// contiguous tile range with the phases in program order and named barriers; the 32 KB of weight tiles are shared.
+// A group owns three 32 KB tile buffers, each reused along the tile:
+//   B1: TMA landing of e_{l-1} (fp32) -> bf16 hi|lo operand in place (G1, G5) -> fp32 staging of d e_{l-1} -> TMA store
+//   B2: TMA landing of d e_l          -> hid operand (G3)                   -> dz1 operand (G5, G6)
+//   B3: TMA landing of e_l            -> dm operand (G3, G4); dm lives in registers while B1 is converted
+// and one 64-column TMEM accumulator that is in turn acc1 (Pi+Pj preloaded by tcgen05.st, + G1), acc4 (G4) and
+// acc6 (G6), plus the two weight-gradient accumulators kept for the whole kernel: 192 columns per group.
+//   G1  acc += e_{l-1} . C^T  (on top of Pi[dst]+Pj[src])     G4  acc  = dm . W2
+//   G3  accW2 += dm^T . hid                                    G5  accC += dz1^T . e_{l-1}      G6  acc = dz1 . C
+// The next tile's e_l / d e_l / e_{l-1} loads are issued as soon as G3/G4, G5/G6 and the store have released their
+// buffers, so they fly during the rest of the tile; the dPj / dPi reds run while G5/G6 execute.
+#define GCRL_MBAR_TIMEOUT   // counted waits: a protocol bug traps instead of hanging the GPU
+#include "gn_common.cuh"
+#include "ws.cuh"
+#include <stdlib.h>
+
+namespace gcrl {
+
+using namespace tc;
+
+constexpr int BG_N = 2;                  // groups per CTA
+constexpr int BG_T = 256;                // threads per group
+
+struct BwdWgSmem {
+    __nv_bfloat16 Wc[2][64 * 64];        // C hi/lo (FIRST: C^T in fp32 [d][o])
+    __nv_bfloat16 W2[2][64 * 64];
+    unsigned char B1[BG_N][32768];
+    unsigned char B2[BG_N][32768];
+    unsigned char B3[BG_N][32768];
+    float bsum[64];
+    uint64_t bar_E[BG_N], bar_M[BG_N], bar_D[BG_N], bar_mma[BG_N];
+    uint32_t tmem_base;
+};
+
+struct BwdWgArgs {
+    const float* Pi; const float* Pj;
+    const float* e_prev; int De;
+    const float* W1; int ldW1, coff;
+    const float* W2;
+    const int32_t* src; const int32_t* dst;
+    int32_t N, E;
+    const float* ca; const float* cb;
+    const float* dagg;
+    const int32_t* amin; const int32_t* amax;
+    float* dPi; float* dPj;
+    float* gW1; float* gW2; float* gb2;
+};
+
+// FIRST: block 1 (raw edge features, no d e_0).  NODE: block 5 (no d e_5: dm = ca + cb e_5 + arg terms).
+template <bool FIRST, bool NODE, bool X3>
+__global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_constant__ CUtensorMap tm_e,
+                                                               const __grid_constant__ CUtensorMap tm_m,
+                                                               const __grid_constant__ CUtensorMap tm_de,
+                                                               const __grid_constant__ CUtensorMap tm_out,
+                                                               const BwdWgArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    BwdWgSmem& S = *reinterpret_cast<BwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
+    const int sp = gw & 3, half = gw >> 2;          // TMEM sub-partition (rows 32sp..) and column half
+    const int row = 32 * sp + lane;                 // this thread's tile row in the epilogues
+    const int bar_id = 1 + grp;
+
+    if (tid == 0) {
+        for (int g = 0; g < BG_N; ++g) {
+            mbar_init(&S.bar_E[g], 1); mbar_init(&S.bar_M[g], 1); mbar_init(&S.bar_D[g], 1); mbar_init(&S.bar_mma[g], 1);
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tm_m);
+        if (!FIRST) { tma_prefetch_desc(&tm_e); tma_prefetch_desc(&tm_out); }
+        if (!NODE) tma_prefetch_desc(&tm_de);
+    }
+    if (tid < 32) tmem_alloc<512>(&S.tmem_base);
+    load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, BG_N * BG_T);
+    if (!FIRST) load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, BG_N * BG_T);
+    float (*Cf)[64] = reinterpret_cast<float (*)[64]>(&S.Wc[0][0]);   // FIRST: C^T fp32 [d][o]
+    if (FIRST) {
+        for (int t = tid; t < a.De * 64; t += BG_N * BG_T) Cf[t >> 6][t & 63] = a.W1[(t & 63) * a.ldW1 + a.coff + (t >> 6)];
+        for (int t = tid; t < BG_N * 32768 / 16; t += BG_N * BG_T)   // zero-padded raw edge-feature operand tiles
+            reinterpret_cast<uint4*>(&S.B1[0][0])[t] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid < 64) S.bsum[tid] = 0.f;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t t_acc = S.tmem_base + 192 * grp, t_w2 = t_acc + 64, t_c = t_acc + 128;
+    const uint32_t lane_addr = (uint32_t)(32 * sp) << 16;
+    const uint32_t id_feat = make_idesc_bf16(128, 64, false, false);
+    const uint32_t id_featT = make_idesc_bf16(128, 64, false, true);
+    const uint32_t id_rows = make_idesc_bf16(64, 64, true, true);
+    const uint32_t wc_hi = smem_u32(S.Wc[0]), wc_lo = smem_u32(S.Wc[1]);
+    const uint32_t w2_hi = smem_u32(S.W2[0]), w2_lo = smem_u32(S.W2[1]);
+    unsigned char* const B1 = S.B1[grp];
+    unsigned char* const B2 = S.B2[grp];
+    unsigned char* const B3 = S.B3[grp];
+    const uint32_t b1_hi = smem_u32(B1), b1_lo = b1_hi + 16384;
+    const uint32_t b2_hi = smem_u32(B2), b2_lo = b2_hi + 16384;
+    const uint32_t b3_hi = smem_u32(B3), b3_lo = b3_hi + 16384;
+    __nv_bfloat16* const B1h = reinterpret_cast<__nv_bfloat16*>(B1);
+    __nv_bfloat16* const B1l = reinterpret_cast<__nv_bfloat16*>(B1 + 16384);
+    __nv_bfloat16* const B2h = reinterpret_cast<__nv_bfloat16*>(B2);
+    __nv_bfloat16* const B2l = reinterpret_cast<__nv_bfloat16*>(B2 + 16384);
+    float* const B1f = reinterpret_cast<float*>(B1);
+    const float* const B2f = reinterpret_cast<const float*>(B2);
+    const float* const B3f = reinterpret_cast<const float*>(B3);
+    uint64_t* const bar_E = &S.bar_E[grp];
+    uint64_t* const bar_M = &S.bar_M[grp];
+    uint64_t* const bar_D = &S.bar_D[grp];
+    uint64_t* const bar_mma = &S.bar_mma[grp];
+    uint32_t ph_E = 0, ph_M = 0, ph_D = 0, ph_mma = 0;
+
+    // contiguous tile ranges: a CTA (and each of its groups) stays inside one or two graphs, so CTAs do not fight over
+    // the same dPi / dPj rows and the Pi / Pj / coefficient gathers stay in L1 / L2
+    const int64_t n_tiles = ((int64_t)a.E + TILE - 1) / TILE;
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t cta_first = (int64_t)blockIdx.x * per_cta;
+    const int n_cta = (int)max((int64_t)0, min(per_cta, n_tiles - cta_first));
+    const int n0 = (n_cta + 1) / 2;
+    const int64_t tile_first = cta_first + (grp ? n0 : 0);
+    const int n_mine = grp ? n_cta - n0 : n0;
+    auto tile_t0 = [&](int i) { return (int32_t)((tile_first + i) * TILE); };
+
+    const uint64_t pol = l2_policy_evict_first();
+    auto load_E = [&](int i) {
+        mbar_arrive_expect_tx(bar_E, 32768);
+        tma_load_2d_hint(B1, &tm_e, 0, tile_t0(i), bar_E, pol);
+        tma_load_2d_hint(B1 + 16384, &tm_e, 32, tile_t0(i), bar_E, pol);
+    };
+    auto load_M = [&](int i) {
+        mbar_arrive_expect_tx(bar_M, 32768);
+        tma_load_2d_hint(B3, &tm_m, 0, tile_t0(i), bar_M, pol);
+        tma_load_2d_hint(B3 + 16384, &tm_m, 32, tile_t0(i), bar_M, pol);
+    };
+    auto load_D = [&](int i) {
+        mbar_arrive_expect_tx(bar_D, 32768);
+        tma_load_2d_hint(B2, &tm_de, 0, tile_t0(i), bar_D, pol);
+        tma_load_2d_hint(B2 + 16384, &tm_de, 32, tile_t0(i), bar_D, pol);
+    };
+    if (gt == 64 && n_mine > 0) {
+        load_M(0);
+        if (!NODE) load_D(0);
+        if (!FIRST) load_E(0);
+    }
+
+    const int cp = 2 * (lane & 3);
+    const int c4 = gt & 15;
+    int32_t cur_d = -1;                            // destination whose Pi row is cached in piv
+    float2 piv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) piv[c] = make_float2(0.f, 0.f);
+    int32_t cur_v = -1;                            // destination whose coefficients are cached in A4 / B4 (...)
+    float4 A4 = make_float4(0.f, 0.f, 0.f, 0.f), B4 = A4, Gmn = A4, Gmx = A4;
+    int4 Imn = make_int4(-1, -1, -1, -1), Imx = Imn;
+    float bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
+
+    for (int i = 0; i < n_mine; ++i) {
+        const int32_t t0 = tile_t0(i);
+        const int nrows = min(TILE, a.E - t0);
+        // ---- Pi[dst] + Pj[src] (+ C e in block 1) -> acc (TMEM), 16x256b fragment layout ------------------------------
+        {
+            const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
+            const bool va = ra < nrows, vb = rb < nrows;
+            const int32_t da = va ? __ldg(a.dst + t0 + ra) : -1, db = vb ? __ldg(a.dst + t0 + rb) : -1;
+            const int32_t sa = va ? __ldg(a.src + t0 + ra) : 0, sb = vb ? __ldg(a.src + t0 + rb) : 0;
+            const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)sa * 64 + cp);
+            const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)sb * 64 + cp);
+            float2 ya[8], yb[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { ya[c] = __ldg(pja + 4 * c); yb[c] = __ldg(pjb + 4 * c); }
+            if (va && da != cur_d) {
+                cur_d = da;
+                const float2* pia = reinterpret_cast<const float2*>(a.Pi + (int64_t)da * 64 + cp);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) piv[c] = __ldg(pia + 4 * c);
+            }
+            const bool b_other = vb && db != cur_d;
+            const float2* pib = reinterpret_cast<const float2*>(a.Pi + (int64_t)(vb ? db : 0) * 64 + cp);
+            float v[32];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float2 xb = piv[c];
+                if (b_other) xb = __ldg(pib + 4 * c);
+                v[4 * c + 0] = va ? piv[c].x + ya[c].x : 0.f;
+                v[4 * c + 1] = va ? piv[c].y + ya[c].y : 0.f;
+                v[4 * c + 2] = vb ? xb.x + yb[c].x : 0.f;
+                v[4 * c + 3] = vb ? xb.y + yb[c].y : 0.f;
+            }
+            if (FIRST) {
+                for (int d = 0; d < a.De; ++d) {
+                    const float ea = va ? a.e_prev[(int64_t)(t0 + ra) * a.De + d] : 0.f;
+                    const float eb = vb ? a.e_prev[(int64_t)(t0 + rb) * a.De + d] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float2 cc = *reinterpret_cast<const float2*>(&Cf[d][8 * c + cp]);
+                        v[4 * c + 0] = fmaf(ea, cc.x, v[4 * c + 0]);
+                        v[4 * c + 1] = fmaf(ea, cc.y, v[4 * c + 1]);
+                        v[4 * c + 2] = fmaf(eb, cc.x, v[4 * c + 2]);
+                        v[4 * c + 3] = fmaf(eb, cc.y, v[4 * c + 3]);
+                    }
+                }
+            }
+            tmem_st_16x256b_x8(t_acc + ((uint32_t)(32 * sp + 16 * half) << 16), v);
+        }
+        tmem_st_wait();
+        // ---- dm = d e_l + ca[v] + cb[v] e_l (+ arg terms in block 5), kept in registers ---------------------------------
+        float4 dm[8];
+        mbar_wait(bar_M, ph_M);
+        ph_M ^= 1;
+        if (!NODE) { mbar_wait(bar_D, ph_D); ph_D ^= 1; }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = (gt >> 4) + 16 * it;
+            const int32_t v = r < nrows ? __ldg(a.dst + t0 + r) : -1;
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v >= 0) {
+                if (v != cur_v) {
+                    cur_v = v;
+                    A4 = __ldg(reinterpret_cast<const float4*>(a.ca + (int64_t)v * 64) + c4);
+                    B4 = __ldg(reinterpret_cast<const float4*>(a.cb + (int64_t)v * 64) + c4);
+                    if (NODE) {
+                        Imn = __ldg(reinterpret_cast<const int4*>(a.amin + (int64_t)v * 64) + c4);
+                        Imx = __ldg(reinterpret_cast<const int4*>(a.amax + (int64_t)v * 64) + c4);
+                        Gmn = __ldg(reinterpret_cast<const float4*>(a.dagg + (int64_t)v * 256 + 64) + c4);
+                        Gmx = __ldg(reinterpret_cast<const float4*>(a.dagg + (int64_t)v * 256 + 128) + c4);
+                    }
+                }
+                const float4 m4 = *reinterpret_cast<const float4*>(l_ptr(B3f, r, c4));
+                float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!NODE) d4 = *reinterpret_cast<const float4*>(l_ptr(B2f, r, c4));
+                r4.x = fmaf(B4.x, m4.x, A4.x) + d4.x; r4.y = fmaf(B4.y, m4.y, A4.y) + d4.y;
+                r4.z = fmaf(B4.z, m4.z, A4.z) + d4.z; r4.w = fmaf(B4.w, m4.w, A4.w) + d4.w;
+                if (NODE) {
+                    const int32_t slot_e = t0 + r;
+                    if (Imn.x == slot_e) r4.x += Gmn.x;
+                    if (Imn.y == slot_e) r4.y += Gmn.y;
+                    if (Imn.z == slot_e) r4.z += Gmn.z;
+                    if (Imn.w == slot_e) r4.w += Gmn.w;
+                    if (Imx.x == slot_e) r4.x += Gmx.x;
+                    if (Imx.y == slot_e) r4.y += Gmx.y;
+                    if (Imx.z == slot_e) r4.z += Gmx.z;
+                    if (Imx.w == slot_e) r4.w += Gmx.w;
+                }
+            }
+            bs0 += r4.x; bs1 += r4.y; bs2 += r4.z; bs3 += r4.w;
+            dm[it] = r4;
+        }
+        // ---- e_{l-1}: fp32 landing tile -> registers; then both operand tiles are written in place ----------------------
+        float4 x[8];
+        if (!FIRST) {
+            mbar_wait(bar_E, ph_E);
+            ph_E ^= 1;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(l_ptr(B1f, (gt >> 4) + 16 * it, c4));
+        }
+        named_sync(bar_id, BG_T);          // every landing row has been read before any operand row is written
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = (gt >> 4) + 16 * it;
+            const uint32_t off = bf_off(r, c4 >> 1) + (c4 & 1) * 8;
+            uint2 h, l;
+            if (!FIRST) {
+                split4<X3>(x[it], h, l);
+                *reinterpret_cast<uint2*>(B1 + off) = h;
+                if (X3) *reinterpret_cast<uint2*>(B1 + 16384 + off) = l;
+            }
+            split4<X3>(dm[it], h, l);
+            *reinterpret_cast<uint2*>(B3 + off) = h;
+            if (X3) *reinterpret_cast<uint2*>(B3 + 16384 + off) = l;
+        }
+        if (FIRST && gt < TILE) {
+            // zero-padded raw edge features: chunk 0 of the row holds e[0..De)
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = (gt < nrows && j < a.De) ? a.e_prev[(int64_t)(t0 + gt) * a.De + j] : 0.f;
+            store_split8<X3>(y, B1h, B1l, gt, 0);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, BG_T);
+        tc_fence_after();
+        if (!FIRST) {
+            if (gw == 0 && elect_one()) {
+                issue_gemm_feat<X3, true>(t_acc, b1_hi, b1_lo, wc_hi, wc_lo, id_feat, true);       // G1
+                umma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, ph_mma);
+            ph_mma ^= 1;
+            tc_fence_after();
+        }
+        // ---- epilogue 1: hid = relu(acc1) -> B2, relu mask in a register ---------------------------------------------------
+        uint32_t hm = 0u;
+        {
+            float acc[32];
+            tmem_ld32(t_acc + lane_addr + 32 * half, acc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    y[j] = fmaxf(acc[8 * c + j], 0.f);
+                    hm |= (acc[8 * c + j] > 0.f ? 1u : 0u) << (8 * c + j);
+                }
+                store_split8<X3>(y, B2h, B2l, row, 4 * half + c);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, BG_T);
+        if (gw == 0 && elect_one()) {
+            tc_fence_after();
+            issue_gemm_rows<X3, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);       // G3
+            issue_gemm_featT<X3, true>(t_acc, b3_hi, b3_lo, w2_hi, w2_lo, id_featT, false);         // G4
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (gt == 64 && i + 1 < n_mine) load_M(i + 1);       // B3 is free: the next tile's e_l flies during the rest of this tile
+        // ---- epilogue 3: dz1 = acc4 * relu' -> B2 (G3 has finished with hid) -----------------------------------------------
+        float dz[32];
+        tmem_ld32(t_acc + lane_addr + 32 * half, dz);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = ((hm >> j) & 1u) ? dz[j] : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) store_split8<X3>(&dz[8 * c], B2h, B2l, row, 4 * half + c);
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, BG_T);
+        if (gw == 0 && elect_one()) {
+            tc_fence_after();
+            issue_gemm_rows<X3, true>(t_c, b2_hi, b2_lo, b1_hi, b1_lo, id_rows, 128, i > 0);        // G5
+            if (!FIRST) issue_gemm_featT<X3, true>(t_acc, b2_hi, b2_lo, wc_hi, wc_lo, id_featT, false);   // G6
+            umma_commit(bar_mma);
+        }
+        // ---- while G5/G6 run: dPj[src] += dz1 (vector reds), dPi[dst] += segment sums (warp transpose-reduce) ---------------
+        {
+            const bool valid = row < nrows;
+            const int32_t my_src = valid ? __ldg(a.src + t0 + row) : 0;
+            const int32_t my_dst = valid ? __ldg(a.dst + t0 + row) : -1;
+            const int32_t dprev = __shfl_up_sync(0xffffffffu, my_dst, 1);
+            const uint32_t sbits = __ballot_sync(0xffffffffu, valid && lane > 0 && my_dst != dprev);
+            const int nb = __popc(sbits);
+            const int32_t d0 = __shfl_sync(0xffffffffu, my_dst, 0);
+            const int bpos = nb ? (__ffs(sbits) - 1) : 0;
+            const int32_t d1 = __shfl_sync(0xffffffffu, my_dst, bpos);
+            if (valid) {
+                float* pj = a.dPj + (int64_t)my_src * 64 + 32 * half;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add_v4(pj + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+            }
+            if (nb == 0) {
+                if (d0 >= 0) {
+                    const float sum = warp_colsum32(dz, lane);
+                    atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * half + lane, sum);
+                }
+            } else if (nb == 1) {
+                float t[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = lane < bpos ? dz[j] : 0.f;
+                const float s0 = warp_colsum32(t, lane);
+                atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * half + lane, s0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dz[j] = (lane >= bpos && valid) ? dz[j] : 0.f;
+                const float s1 = warp_colsum32(dz, lane);
+                atomicAdd(a.dPi + (int64_t)d1 * 64 + 32 * half + lane, s1);
+            } else if (valid) {
+                float* pi = a.dPi + (int64_t)my_dst * 64 + 32 * half;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add_v4(pi + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+            }
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (!NODE && gt == 64 && i + 1 < n_mine) load_D(i + 1);     // B2 is free
+        // ---- epilogue 4: d e_{l-1} = acc6 -> fp32 staging in B1 (G5 has finished with it) -> TMA store -----------------------
+        if (!FIRST) {
+            float acc[32];
+            tmem_ld32(t_acc + lane_addr + 32 * half, acc);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(l_ptr(B1f, row, 8 * half + c)) = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            fence_proxy_async();
+            tc_fence_before();
+            named_sync(bar_id, BG_T);
+            if (gt == 64) {
+                tma_store_2d_hint(&tm_out, 0, t0, B1f, pol);              // rows past E are clipped by the tensor map
+                tma_store_2d_hint(&tm_out, 32, t0, B1f + 128 * 32, pol);
+                bulk_commit();
+                bulk_wait_read0();
+                if (i + 1 < n_mine) load_E(i + 1);
+            }
+        } else {
+            tc_fence_before();
+            named_sync(bar_id, BG_T);      // every epilogue read of acc precedes the next tile's tcgen05.st
+        }
+    }
+    if (!FIRST && gt == 64) bulk_wait0();
+    // ---- weight gradients: TMEM -> global (one atomic pass per group), bias gradient ---------------------------------------------
+    tc_fence_after();
+    if (n_mine > 0) {
+        const int o = 16 * sp + lane;          // accumulator row of an M = 64 product (lanes 0..15 of each sub-partition)
+        float v[32];
+        tmem_ld32(t_w2 + lane_addr + 32 * half, v);
+        if (lane < 16)
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add_v4(&a.gW2[o * 64 + 32 * half + j], v[j], v[j + 1], v[j + 2], v[j + 3]);
+        tmem_ld32(t_c + lane_addr + 32 * half, v);
+        if (lane < 16) {
+            if (!FIRST) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(&a.gW1[o * a.ldW1 + a.coff + 32 * half + j], v[j]);
+            } else if (half == 0) {
+                for (int j = 0; j < a.De; ++j) atomicAdd(&a.gW1[o * a.ldW1 + a.coff + j], v[j]);
+            }
+        }
+    }
+    atomicAdd(&S.bsum[4 * c4 + 0], bs0); atomicAdd(&S.bsum[4 * c4 + 1], bs1);
+    atomicAdd(&S.bsum[4 * c4 + 2], bs2); atomicAdd(&S.bsum[4 * c4 + 3], bs3);
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 64) atomicAdd(&a.gb2[tid], S.bsum[tid]);
+    if (tid < 32) tmem_dealloc<512>(S.tmem_base);
+}
+
+template <bool FIRST, bool NODE, bool X3>
+static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, const CUtensorMap& tde, const CUtensorMap& tout,
+                                 const BwdWgArgs& a, int grid, cudaStream_t st) {
+    const int smem = (int)sizeof(BwdWgSmem) + 1024;
+    static bool done = false;
+    if (!done) {
+        GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        done = true;
+    }
+    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, a);
+    return GCRL_OK;
+}
+
+// GCRL_EDGE_IMPL: "wg" this kernel, "ws" the warp-specialised pipeline, "tc" the single-group kernel
+int bwd_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GCRL_EDGE_IMPL");
+        v = 0;
+        if (e && e[0] == 'w' && e[1] == 's') v = 1;
+        if (e && e[0] == 't' && e[1] == 'c') v = 2;
+    }
+    return v;
+}
+
+// Two-group tensor-core edge backward of one block; same contract as launch_edge_bwd_ws (m must be given: the
+// recompute flavour of block 5 stays on the other kernels).
+int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
+                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
+                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
+                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st) {
+    (void)seg_off; (void)b2;
+    if (E == 0) return GCRL_OK;
+    GCRL_CHECK_ARG(m != nullptr);
+    const bool no_de = (de == nullptr);
+    GCRL_CHECK_ARG(!(first && no_de));
+    BwdWgArgs a;
+    a.Pi = Pi; a.Pj = Pj; a.e_prev = e_prev; a.De = De;
+    a.W1 = W1; a.ldW1 = ldW1; a.coff = coff; a.W2 = W2;
+    a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
+    a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
+    a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
+    CUtensorMap te, tm, tde, tout;
+    int rc;
+    // unused maps point at a valid [N,64] array so that encoding never fails
+    if ((rc = make_tmap_rows64(&te, first ? Pi : e_prev, first ? N : E, 128))) return rc;
+    if ((rc = make_tmap_rows64(&tm, m, E, 128))) return rc;
+    if ((rc = make_tmap_rows64(&tde, no_de ? Pi : de, no_de ? N : E, 128))) return rc;
+    if ((rc = make_tmap_rows64(&tout, first ? Pi : de_prev, first ? N : E, 128))) return rc;
+    const int64_t tiles = (E + TILE - 1) / TILE;
+    const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
+    const int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
+    const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (no_de ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
+    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, a, (int)grid, st)
+                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, a, (int)grid, st);
+    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, a, (int)grid, st)
+                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, a, (int)grid, st);
+    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, a, (int)grid, st)
+                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, a, (int)grid, st);
+    prof_end(tok, st);
+    if (rc) return rc;
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+}  // namespace gcrl

@@ -74,7 +74,7 @@ struct BwdWsArgs {
     float* gW1; float* gW2; float* gb2;
     int no_de;                                // block 5: there is no d e_l (dm = ca + cb e_l + arg terms, applied here)
     int pf;                                   // L2 prefetch distance in tiles (0 = off)
-    int dbg;                                  // timing experiments only (GCRL_WS_DBG): 1 no reds, 2 no gather, 4 no store, 8 single-pass bf16 weight-gradient products
+    int dbg;                                  // timing experiments only (GCRL_WS_DBG): 1 no reds, 2 no gather, 4 no store, 8 single-pass bf16 weight-gradient products, 16 no dPj reds, 32 no dPi reds
     long long* trace;                         // debugging: clock64 per (role, tile, event) of CTA 0, or null
 };
 
@@ -731,16 +731,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_edge_bwd_ws(const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 32; ++j) acc[j] = ((hm >> j) & 1u) ? acc[j] : 0.f;
                         if (a.dbg & 1) continue;
-                        if (valid) {
+                        if (valid && !(a.dbg & 16)) {
                             float* pj = a.dPj + (int64_t)my_src * 64 + 32 * hf;
 #pragma unroll
                             for (int c = 0; c < 8; ++c) red_add_v4(pj + 4 * c, acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
                         }
+                        if (a.dbg & 32) continue;
                         if (nb == 0) {
                             if (d0 >= 0) {
                                 const float sum = warp_colsum32(acc, lane);
                                 atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * hf + lane, sum);
                             }
+                        } else if (nb == 1) {
+                            // one boundary inside the warp's 32 rows: two masked column sums instead of 32 lanes
+                            // hammering two dPi rows with reds (same-address atomics serialise in L2)
+                            float t[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) t[j] = lane < bpos ? acc[j] : 0.f;
+                            const float sa = warp_colsum32(t, lane);
+                            atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * hf + lane, sa);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = (lane >= bpos && valid) ? acc[j] : 0.f;
+                            const float sb = warp_colsum32(acc, lane);
+                            atomicAdd(a.dPi + (int64_t)d1 * 64 + 32 * hf + lane, sb);
                         } else if (valid) {
                             float* pi = a.dPi + (int64_t)my_dst * 64 + 32 * hf;
 #pragma unroll
