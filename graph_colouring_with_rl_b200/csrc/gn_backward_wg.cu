@@ -28,6 +28,14 @@ namespace gcrl {
 
 using namespace tc;
 
+// phase timeline of group 0 of CTA 0 (diagnostic build: GCRL_NVCC_FLAGS=-DGCRL_BWD_TRACE_BUILD): cycles per phase
+// averaged over the group's tiles, printed at the end of the kernel
+#ifdef GCRL_BWD_TRACE_BUILD
+#define BW_TR(k) do { if (tid == 0 && blockIdx.x == 0) { const long long c_ = clock64(); tr_acc[k] += c_ - tr_last; tr_last = c_; } } while (0)
+#else
+#define BW_TR(k) do { } while (0)
+#endif
+
 constexpr int BG_N = 2;                  // groups per CTA
 constexpr int BG_T = 256;                // threads per group
 
@@ -94,6 +102,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t t_acc = S.tmem_base + 192 * grp, t_w2 = t_acc + 64, t_c = t_acc + 128;
+    const uint32_t t_hm = S.tmem_base + 384 + 2 * grp;
     const uint32_t lane_addr = (uint32_t)(32 * sp) << 16;
     const uint32_t id_feat = make_idesc_bf16(128, 64, false, false);
     const uint32_t id_featT = make_idesc_bf16(128, 64, false, true);
@@ -163,15 +172,47 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
     int4 Imn = make_int4(-1, -1, -1, -1), Imx = Imn;
     float bs0 = 0.f, bs1 = 0.f, bs2 = 0.f, bs3 = 0.f;
 
+#ifdef GCRL_BWD_TRACE_BUILD
+    long long tr_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
+#endif
+    // endpoint ids of the fragment rows (ra, ra + 8) of the gather, one tile ahead of their use
+    int32_t nda = -1, ndb = -1, nsa = 0, nsb = 0;
+    auto gather_ids = [&](int i) {
+        nda = -1; ndb = -1; nsa = 0; nsb = 0;
+        if (i < n_mine) {
+            const int32_t t0 = tile_t0(i);
+            const int nrows = min(TILE, a.E - t0);
+            const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
+            if (ra < nrows) { nda = __ldg(a.dst + t0 + ra); nsa = __ldg(a.src + t0 + ra); }
+            if (rb < nrows) { ndb = __ldg(a.dst + t0 + rb); nsb = __ldg(a.src + t0 + rb); }
+        }
+    };
+    gather_ids(0);
     for (int i = 0; i < n_mine; ++i) {
         const int32_t t0 = tile_t0(i);
         const int nrows = min(TILE, a.E - t0);
+        BW_TR(0);
+        int32_t sa_cur = 0, sb_cur = 0;
+        bool sa_ok = false, sb_ok = false;
+        // every endpoint id this thread needs during the tile, fetched in one batch: with 225 KB of the SM's 256 KB
+        // configured as shared memory the L1 keeps next to nothing, and an id load inside a phase costs that phase an
+        // L2 round trip (the dm loop spent 5 000 cycles per tile on eight serialised ones)
+        int32_t vv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = (gt >> 4) + 16 * it;
+            vv[it] = r < nrows ? __ldg(a.dst + t0 + r) : -1;
+        }
+        const bool valid = row < nrows;
+        const int32_t my_src = valid ? __ldg(a.src + t0 + row) : 0;
+        const int32_t my_dst = valid ? __ldg(a.dst + t0 + row) : -1;
         // ---- Pi[dst] + Pj[src] (+ C e in block 1) -> acc (TMEM), 16x256b fragment layout ------------------------------
         {
             const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
             const bool va = ra < nrows, vb = rb < nrows;
-            const int32_t da = va ? __ldg(a.dst + t0 + ra) : -1, db = vb ? __ldg(a.dst + t0 + rb) : -1;
-            const int32_t sa = va ? __ldg(a.src + t0 + ra) : 0, sb = vb ? __ldg(a.src + t0 + rb) : 0;
+            const int32_t da = nda, db = ndb, sa = nsa, sb = nsb;       // fetched one tile ahead
+            sa_cur = sa; sb_cur = sb; sa_ok = va; sb_ok = vb;
+            gather_ids(i + 1);
             const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)sa * 64 + cp);
             const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)sb * 64 + cp);
             float2 ya[8], yb[8];
@@ -212,15 +253,17 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             tmem_st_16x256b_x8(t_acc + ((uint32_t)(32 * sp + 16 * half) << 16), v);
         }
         tmem_st_wait();
+        BW_TR(1);
         // ---- dm = d e_l + ca[v] + cb[v] e_l (+ arg terms in block 5), kept in registers ---------------------------------
         float4 dm[8];
         mbar_wait(bar_M, ph_M);
         ph_M ^= 1;
         if (!NODE) { mbar_wait(bar_D, ph_D); ph_D ^= 1; }
+        BW_TR(2);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = (gt >> 4) + 16 * it;
-            const int32_t v = r < nrows ? __ldg(a.dst + t0 + r) : -1;
+            const int32_t v = vv[it];
             float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (v >= 0) {
                 if (v != cur_v) {
@@ -256,13 +299,16 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         }
         // ---- e_{l-1}: fp32 landing tile -> registers; then both operand tiles are written in place ----------------------
         float4 x[8];
+        BW_TR(3);
         if (!FIRST) {
             mbar_wait(bar_E, ph_E);
             ph_E ^= 1;
+            BW_TR(4);
 #pragma unroll
             for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(l_ptr(B1f, (gt >> 4) + 16 * it, c4));
         }
         named_sync(bar_id, BG_T);          // every landing row has been read before any operand row is written
+        BW_TR(5);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = (gt >> 4) + 16 * it;
@@ -288,6 +334,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         tc_fence_before();
         named_sync(bar_id, BG_T);
         tc_fence_after();
+        BW_TR(6);
         if (!FIRST) {
             if (gw == 0 && elect_one()) {
                 issue_gemm_feat<X3, true>(t_acc, b1_hi, b1_lo, wc_hi, wc_lo, id_feat, true);       // G1
@@ -297,6 +344,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             ph_mma ^= 1;
             tc_fence_after();
         }
+        BW_TR(7);
         // ---- epilogue 1: hid = relu(acc1) -> B2, relu mask in a register ---------------------------------------------------
         uint32_t hm = 0u;
         {
@@ -313,9 +361,12 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 store_split8<X3>(y, B2h, B2l, row, 4 * half + c);
             }
         }
+        tmem_st_x1(t_hm + half + lane_addr, hm);     // relu mask of (row, column half): the dPj reds read it in fragment layout
+        tmem_st_wait();
         fence_proxy_async();
         tc_fence_before();
         named_sync(bar_id, BG_T);
+        BW_TR(8);
         if (gw == 0 && elect_one()) {
             tc_fence_after();
             issue_gemm_rows<X3, true>(t_w2, b3_hi, b3_lo, b2_hi, b2_lo, id_rows, 128, i > 0);       // G3
@@ -325,6 +376,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        BW_TR(9);
         if (gt == 64 && i + 1 < n_mine) load_M(i + 1);       // B3 is free: the next tile's e_l flies during the rest of this tile
         // ---- epilogue 3: dz1 = acc4 * relu' -> B2 (G3 has finished with hid) -----------------------------------------------
         float dz[32];
@@ -335,7 +387,30 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         for (int c = 0; c < 4; ++c) store_split8<X3>(&dz[8 * c], B2h, B2l, row, 4 * half + c);
         fence_proxy_async();
         tc_fence_before();
+        // dz1 once more, in the 16x256b fragment layout (thread: rows ra, ra + 8, column pairs 8c + cp), for the dPj
+        // reds: a quad of lanes covers one 32-byte sector, an instruction 8 full sectors (the row-per-lane layout of the
+        // epilogue would touch 32 lines with 16 bytes each)
+        float dzf[32];
+        {
+            tmem_ld_16x256b_x8(t_acc + ((uint32_t)(32 * sp + 16 * half) << 16), dzf);
+            uint32_t m0, m1;
+            tmem_ld_x2(t_hm + lane_addr, m0, m1);                 // this lane's row: masks of columns 0-31, 32-63
+            const int la = 16 * half + (lane >> 2), lb = la + 8;  // lanes of this warp that own rows ra, rb
+            const uint32_t a0 = __shfl_sync(0xffffffffu, m0, la), a1 = __shfl_sync(0xffffffffu, m1, la);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, m0, lb), b1 = __shfl_sync(0xffffffffu, m1, lb);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t wa = c < 4 ? a0 : a1, wb = c < 4 ? b0 : b1;
+                const int bit = 8 * (c & 3) + cp;
+                dzf[4 * c + 0] = ((wa >> bit) & 1u) ? dzf[4 * c + 0] : 0.f;
+                dzf[4 * c + 1] = ((wa >> (bit + 1)) & 1u) ? dzf[4 * c + 1] : 0.f;
+                dzf[4 * c + 2] = ((wb >> bit) & 1u) ? dzf[4 * c + 2] : 0.f;
+                dzf[4 * c + 3] = ((wb >> (bit + 1)) & 1u) ? dzf[4 * c + 3] : 0.f;
+            }
+        }
+        tc_fence_before();
         named_sync(bar_id, BG_T);
+        BW_TR(10);
         if (gw == 0 && elect_one()) {
             tc_fence_after();
             issue_gemm_rows<X3, true>(t_c, b2_hi, b2_lo, b1_hi, b1_lo, id_rows, 128, i > 0);        // G5
@@ -344,20 +419,26 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         }
         // ---- while G5/G6 run: dPj[src] += dz1 (vector reds), dPi[dst] += segment sums (warp transpose-reduce) ---------------
         {
-            const bool valid = row < nrows;
-            const int32_t my_src = valid ? __ldg(a.src + t0 + row) : 0;
-            const int32_t my_dst = valid ? __ldg(a.dst + t0 + row) : -1;
+            {
+                // rows ra / rb of this thread's fragment: their sources were fetched for the gather (sa_cur, sb_cur)
+                if (sa_ok) {
+                    float* pj = a.dPj + (int64_t)sa_cur * 64 + cp;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c], dzf[4 * c + 1]);
+                }
+                if (sb_ok) {
+                    float* pj = a.dPj + (int64_t)sb_cur * 64 + cp;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c + 2], dzf[4 * c + 3]);
+                }
+            }
             const int32_t dprev = __shfl_up_sync(0xffffffffu, my_dst, 1);
             const uint32_t sbits = __ballot_sync(0xffffffffu, valid && lane > 0 && my_dst != dprev);
             const int nb = __popc(sbits);
             const int32_t d0 = __shfl_sync(0xffffffffu, my_dst, 0);
             const int bpos = nb ? (__ffs(sbits) - 1) : 0;
             const int32_t d1 = __shfl_sync(0xffffffffu, my_dst, bpos);
-            if (valid) {
-                float* pj = a.dPj + (int64_t)my_src * 64 + 32 * half;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) red_add_v4(pj + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
-            }
+            (void)my_src;
             if (nb == 0) {
                 if (d0 >= 0) {
                     const float sum = warp_colsum32(dz, lane);
@@ -379,9 +460,11 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 for (int c = 0; c < 8; ++c) red_add_v4(pi + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
             }
         }
+        BW_TR(11);
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        BW_TR(12);
         if (!NODE && gt == 64 && i + 1 < n_mine) load_D(i + 1);     // B2 is free
         // ---- epilogue 4: d e_{l-1} = acc6 -> fp32 staging in B1 (G5 has finished with it) -> TMA store -----------------------
         if (!FIRST) {
@@ -393,6 +476,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             fence_proxy_async();
             tc_fence_before();
             named_sync(bar_id, BG_T);
+            BW_TR(13);
             if (gt == 64) {
                 tma_store_2d_hint(&tm_out, 0, t0, B1f, pol);              // rows past E are clipped by the tensor map
                 tma_store_2d_hint(&tm_out, 32, t0, B1f + 128 * 32, pol);
@@ -405,6 +489,13 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             named_sync(bar_id, BG_T);      // every epilogue read of acc precedes the next tile's tcgen05.st
         }
     }
+#ifdef GCRL_BWD_TRACE_BUILD
+    if (tid == 0 && blockIdx.x == 0 && n_mine > 0)
+        printf("bwd_wg<%d,%d,%d> grp0 %d tiles, cycles/tile: top %lld gather %lld waitMD %lld dm %lld waitE %lld xread+sync %lld write+sync %lld g1 %lld ep1+sync %lld g3g4 %lld ep3+sync %lld reds %lld g5g6 %lld ep4+sync %lld\n",
+               (int)FIRST, (int)NODE, (int)X3, n_mine, tr_acc[0] / n_mine, tr_acc[1] / n_mine, tr_acc[2] / n_mine, tr_acc[3] / n_mine, tr_acc[4] / n_mine,
+               tr_acc[5] / n_mine, tr_acc[6] / n_mine, tr_acc[7] / n_mine, tr_acc[8] / n_mine, tr_acc[9] / n_mine, tr_acc[10] / n_mine,
+               tr_acc[11] / n_mine, tr_acc[12] / n_mine, tr_acc[13] / n_mine);
+#endif
     if (!FIRST && gt == 64) bulk_wait0();
     // ---- weight gradients: TMEM -> global (one atomic pass per group), bias gradient ---------------------------------------------
     tc_fence_after();

@@ -32,6 +32,20 @@ __device__ __forceinline__ void tmem_st_16x256b_x8(uint32_t taddr, const float v
           "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
         : "memory");
 }
+// tcgen05.ld counterpart: 16 lanes x 64 columns in the 16x256b fragment layout (same register <-> element map)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float v[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // two 32-bit columns per lane (thread i <-> lane base + i): the relu mask of a tile row
 __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t a0, uint32_t a1) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a0), "r"(a1) : "memory");
@@ -62,6 +76,9 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b));
 }
 
 
