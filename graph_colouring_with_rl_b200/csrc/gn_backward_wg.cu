@@ -62,6 +62,7 @@ struct BwdWgArgs {
     const int32_t* amin; const int32_t* amax;
     float* dPi; float* dPj;
     float* gW1; float* gW2; float* gb2;
+    int dbg;                                  // timing experiments only (GCRL_WS_DBG): 16 no dPj reds, 32 no dPi reds, 2 no gather
 };
 
 // FIRST: block 1 (raw edge features, no d e_0).  NODE: block 5 (no d e_5: dm = ca + cb e_5 + arg terms).
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         // ---- Pi[dst] + Pj[src] (+ C e in block 1) -> acc (TMEM), 16x256b fragment layout ------------------------------
         {
             const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
-            const bool va = ra < nrows, vb = rb < nrows;
+            const bool va = ra < nrows && !(a.dbg & 2), vb = rb < nrows && !(a.dbg & 2);
             const int32_t da = nda, db = ndb, sa = nsa, sb = nsb;       // fetched one tile ahead
             sa_cur = sa; sb_cur = sb; sa_ok = va; sb_ok = vb;
             gather_ids(i + 1);
@@ -421,12 +422,12 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         {
             {
                 // rows ra / rb of this thread's fragment: their sources were fetched for the gather (sa_cur, sb_cur)
-                if (sa_ok) {
+                if (sa_ok && !(a.dbg & 16)) {
                     float* pj = a.dPj + (int64_t)sa_cur * 64 + cp;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c], dzf[4 * c + 1]);
                 }
-                if (sb_ok) {
+                if (sb_ok && !(a.dbg & 16)) {
                     float* pj = a.dPj + (int64_t)sb_cur * 64 + cp;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c + 2], dzf[4 * c + 3]);
@@ -439,7 +440,8 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             const int bpos = nb ? (__ffs(sbits) - 1) : 0;
             const int32_t d1 = __shfl_sync(0xffffffffu, my_dst, bpos);
             (void)my_src;
-            if (nb == 0) {
+            if (a.dbg & 32) {
+            } else if (nb == 0) {
                 if (d0 >= 0) {
                     const float sum = warp_colsum32(dz, lane);
                     atomicAdd(a.dPi + (int64_t)d0 * 64 + 32 * half + lane, sum);
@@ -567,6 +569,7 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
     CUtensorMap te, tm, tde, tout;
     int rc;
     // unused maps point at a valid [N,64] array so that encoding never fails
