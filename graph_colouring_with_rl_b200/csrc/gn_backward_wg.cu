@@ -36,6 +36,11 @@ using namespace tc;
 #define BW_TR(k) do { } while (0)
 #endif
 
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+
 constexpr int BG_N = 2;                  // groups per CTA
 constexpr int BG_T = 256;                // threads per group
 
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                                                                const __grid_constant__ CUtensorMap tm_m,
                                                                const __grid_constant__ CUtensorMap tm_de,
                                                                const __grid_constant__ CUtensorMap tm_out,
+                                                               const __grid_constant__ CUtensorMap tm_dpj,
                                                                const BwdWgArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdWgSmem& S = *reinterpret_cast<BwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -103,7 +109,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t t_acc = S.tmem_base + 192 * grp, t_w2 = t_acc + 64, t_c = t_acc + 128;
-    const uint32_t t_hm = S.tmem_base + 384 + 2 * grp;
     const uint32_t lane_addr = (uint32_t)(32 * sp) << 16;
     const uint32_t id_feat = make_idesc_bf16(128, 64, false, false);
     const uint32_t id_featT = make_idesc_bf16(128, 64, false, true);
@@ -193,8 +198,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         const int32_t t0 = tile_t0(i);
         const int nrows = min(TILE, a.E - t0);
         BW_TR(0);
-        int32_t sa_cur = 0, sb_cur = 0;
-        bool sa_ok = false, sb_ok = false;
         // every endpoint id this thread needs during the tile, fetched in one batch: with 225 KB of the SM's 256 KB
         // configured as shared memory the L1 keeps next to nothing, and an id load inside a phase costs that phase an
         // L2 round trip (the dm loop spent 5 000 cycles per tile on eight serialised ones)
@@ -212,7 +215,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
             const bool va = ra < nrows && !(a.dbg & 2), vb = rb < nrows && !(a.dbg & 2);
             const int32_t da = nda, db = ndb, sa = nsa, sb = nsb;       // fetched one tile ahead
-            sa_cur = sa; sb_cur = sb; sa_ok = va; sb_ok = vb;
             gather_ids(i + 1);
             const float2* pja = reinterpret_cast<const float2*>(a.Pj + (int64_t)sa * 64 + cp);
             const float2* pjb = reinterpret_cast<const float2*>(a.Pj + (int64_t)sb * 64 + cp);
@@ -362,8 +364,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 store_split8<X3>(y, B2h, B2l, row, 4 * half + c);
             }
         }
-        tmem_st_x1(t_hm + half + lane_addr, hm);     // relu mask of (row, column half): the dPj reds read it in fragment layout
-        tmem_st_wait();
         fence_proxy_async();
         tc_fence_before();
         named_sync(bar_id, BG_T);
@@ -378,7 +378,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         ph_mma ^= 1;
         tc_fence_after();
         BW_TR(9);
-        if (gt == 64 && i + 1 < n_mine) load_M(i + 1);       // B3 is free: the next tile's e_l flies during the rest of this tile
         // ---- epilogue 3: dz1 = acc4 * relu' -> B2 (G3 has finished with hid) -----------------------------------------------
         float dz[32];
         tmem_ld32(t_acc + lane_addr + 32 * half, dz);
@@ -386,29 +385,15 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         for (int j = 0; j < 32; ++j) dz[j] = ((hm >> j) & 1u) ? dz[j] : 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) store_split8<X3>(&dz[8 * c], B2h, B2l, row, 4 * half + c);
+        {
+            // fp32 copy of dz1 in B3 (dm is dead: G3/G4 are done) for the dPj reduces below
+            float* B3w = reinterpret_cast<float*>(B3);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(l_ptr(B3w, row, 8 * half + c)) = make_float4(dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+        }
         fence_proxy_async();
         tc_fence_before();
-        // dz1 once more, in the 16x256b fragment layout (thread: rows ra, ra + 8, column pairs 8c + cp), for the dPj
-        // reds: a quad of lanes covers one 32-byte sector, an instruction 8 full sectors (the row-per-lane layout of the
-        // epilogue would touch 32 lines with 16 bytes each)
-        float dzf[32];
-        {
-            tmem_ld_16x256b_x8(t_acc + ((uint32_t)(32 * sp + 16 * half) << 16), dzf);
-            uint32_t m0, m1;
-            tmem_ld_x2(t_hm + lane_addr, m0, m1);                 // this lane's row: masks of columns 0-31, 32-63
-            const int la = 16 * half + (lane >> 2), lb = la + 8;  // lanes of this warp that own rows ra, rb
-            const uint32_t a0 = __shfl_sync(0xffffffffu, m0, la), a1 = __shfl_sync(0xffffffffu, m1, la);
-            const uint32_t b0 = __shfl_sync(0xffffffffu, m0, lb), b1 = __shfl_sync(0xffffffffu, m1, lb);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint32_t wa = c < 4 ? a0 : a1, wb = c < 4 ? b0 : b1;
-                const int bit = 8 * (c & 3) + cp;
-                dzf[4 * c + 0] = ((wa >> bit) & 1u) ? dzf[4 * c + 0] : 0.f;
-                dzf[4 * c + 1] = ((wa >> (bit + 1)) & 1u) ? dzf[4 * c + 1] : 0.f;
-                dzf[4 * c + 2] = ((wb >> bit) & 1u) ? dzf[4 * c + 2] : 0.f;
-                dzf[4 * c + 3] = ((wb >> (bit + 1)) & 1u) ? dzf[4 * c + 3] : 0.f;
-            }
-        }
         tc_fence_before();
         named_sync(bar_id, BG_T);
         BW_TR(10);
@@ -420,18 +405,13 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         }
         // ---- while G5/G6 run: dPj[src] += dz1 (vector reds), dPi[dst] += segment sums (warp transpose-reduce) ---------------
         {
-            {
-                // rows ra / rb of this thread's fragment: their sources were fetched for the gather (sa_cur, sb_cur)
-                if (sa_ok && !(a.dbg & 16)) {
-                    float* pj = a.dPj + (int64_t)sa_cur * 64 + cp;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c], dzf[4 * c + 1]);
-                }
-                if (sb_ok && !(a.dbg & 16)) {
-                    float* pj = a.dPj + (int64_t)sb_cur * 64 + cp;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) red_add_v2(pj + 8 * c, dzf[4 * c + 2], dzf[4 * c + 3]);
-                }
+            // dPj[src] += dz1: one TMA tensor reduce per (row, 32-column half) from the fp32 staging tile in B3 (box
+            // {32, 1} of the dPj tensor map; SWIZZLE_128B is a function of the shared-memory address, so a one-row box
+            // at the row's address undoes the staging tile's XOR pattern).  LSU reds -- 16 or 32 bytes per lane into
+            // 32 / 8 different lines per instruction -- cost 0.9 ms per launch; these run in the TMA / L2 reduce path
+            if (valid && !(a.dbg & 16)) {
+                tma_reduce_add_2d(&tm_dpj, 32 * half, my_src, B3 + half * 16384 + row * 128);
+                bulk_commit();
             }
             const int32_t dprev = __shfl_up_sync(0xffffffffu, my_dst, 1);
             const uint32_t sbits = __ballot_sync(0xffffffffu, valid && lane > 0 && my_dst != dprev);
@@ -439,7 +419,6 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             const int32_t d0 = __shfl_sync(0xffffffffu, my_dst, 0);
             const int bpos = nb ? (__ffs(sbits) - 1) : 0;
             const int32_t d1 = __shfl_sync(0xffffffffu, my_dst, bpos);
-            (void)my_src;
             if (a.dbg & 32) {
             } else if (nb == 0) {
                 if (d0 >= 0) {
@@ -469,6 +448,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         BW_TR(12);
         if (!NODE && gt == 64 && i + 1 < n_mine) load_D(i + 1);     // B2 is free
         // ---- epilogue 4: d e_{l-1} = acc6 -> fp32 staging in B1 (G5 has finished with it) -> TMA store -----------------------
+        bulk_wait_read0();                             // this thread's dPj reduce has read its staging row
         if (!FIRST) {
             float acc[32];
             tmem_ld32(t_acc + lane_addr + 32 * half, acc);
@@ -479,6 +459,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             tc_fence_before();
             named_sync(bar_id, BG_T);
             BW_TR(13);
+            if (gt == 96 && i + 1 < n_mine) load_M(i + 1);          // B3 (dz1 staging) is free: the next tile's e_l
             if (gt == 64) {
                 tma_store_2d_hint(&tm_out, 0, t0, B1f, pol);              // rows past E are clipped by the tensor map
                 tma_store_2d_hint(&tm_out, 32, t0, B1f + 128 * 32, pol);
@@ -489,6 +470,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         } else {
             tc_fence_before();
             named_sync(bar_id, BG_T);      // every epilogue read of acc precedes the next tile's tcgen05.st
+            if (gt == 96 && i + 1 < n_mine) load_M(i + 1);
         }
     }
 #ifdef GCRL_BWD_TRACE_BUILD
@@ -499,6 +481,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                tr_acc[11] / n_mine, tr_acc[12] / n_mine, tr_acc[13] / n_mine);
 #endif
     if (!FIRST && gt == 64) bulk_wait0();
+    bulk_wait0();
     // ---- weight gradients: TMEM -> global (one atomic pass per group), bias gradient ---------------------------------------------
     tc_fence_after();
     if (n_mine > 0) {
@@ -528,14 +511,14 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
 
 template <bool FIRST, bool NODE, bool X3>
 static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, const CUtensorMap& tde, const CUtensorMap& tout,
-                                 const BwdWgArgs& a, int grid, cudaStream_t st) {
+                                 const CUtensorMap& tdpj, const BwdWgArgs& a, int grid, cudaStream_t st) {
     const int smem = (int)sizeof(BwdWgSmem) + 1024;
     static bool done = false;
     if (!done) {
         GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, a);
+    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, tdpj, a);
     return GCRL_OK;
 }
 
@@ -570,23 +553,24 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
-    CUtensorMap te, tm, tde, tout;
+    CUtensorMap te, tm, tde, tout, tdpj;
     int rc;
     // unused maps point at a valid [N,64] array so that encoding never fails
     if ((rc = make_tmap_rows64(&te, first ? Pi : e_prev, first ? N : E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tm, m, E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tde, no_de ? Pi : de, no_de ? N : E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tout, first ? Pi : de_prev, first ? N : E, 128))) return rc;
+    if ((rc = make_tmap_rows64(&tdpj, dPj, N, 1))) return rc;
     const int64_t tiles = (E + TILE - 1) / TILE;
     const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
     const int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (no_de ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
-    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, a, (int)grid, st)
-                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, a, (int)grid, st);
-    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, a, (int)grid, st)
-                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, a, (int)grid, st);
-    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, a, (int)grid, st)
-                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, a, (int)grid, st);
+    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
+                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
+    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
+                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
+    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
+                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
     prof_end(tok, st);
     if (rc) return rc;
     GCRL_LAUNCH_CHECK();

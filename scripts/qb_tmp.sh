@@ -1,2 +1,8 @@
-timeout 900 python -m pytest tests -q -x -m gpu --timeout 300 2>&1 | tail -6
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python -m pytest tests/test_kernels_gpu.py -q -x --timeout 120 -k "backward or learn_step" 2>&1 | tail -3
+run() { timeout 300 python bench.py --graphs 1024 --micro-graphs 512 --skip-extras --steps 2 --warmup 1 --math $1 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print('$1 DBG=$GCRL_WS_DBG', round(d['value']), round(d['ms_per_step'],1), {k:(round(v['avg_ms'],3), round(v['gbps'])) for k,v in d['kernels'].items() if 'bwd' in k})"; }
+run bf16x3
+GCRL_WS_DBG=16 run bf16x3
+GCRL_WS_DBG=48 run bf16x3
