@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                                                                const __grid_constant__ CUtensorMap tm_de,
                                                                const __grid_constant__ CUtensorMap tm_out,
                                                                const __grid_constant__ CUtensorMap tm_dpj,
+                                                               const __grid_constant__ CUtensorMap tm_dpj8,
                                                                const BwdWgArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdWgSmem& S = *reinterpret_cast<BwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
@@ -409,9 +410,21 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             // {32, 1} of the dPj tensor map; SWIZZLE_128B is a function of the shared-memory address, so a one-row box
             // at the row's address undoes the staging tile's XOR pattern).  LSU reds -- 16 or 32 bytes per lane into
             // 32 / 8 different lines per instruction -- cost 0.9 ms per launch; these run in the TMA / L2 reduce path
-            if (valid && !(a.dbg & 16)) {
-                tma_reduce_add_2d(&tm_dpj, 32 * half, my_src, B3 + half * 16384 + row * 128);
-                bulk_commit();
+            // Eight tile rows whose sources are consecutive vertices (the rule inside a segment of a complete graph, except
+            // across the gap at the destination itself) go as ONE eight-row box.
+            if (!(a.dbg & 16)) {
+                const int32_t s_next = __shfl_down_sync(0xffffffffu, my_src, 1);
+                const uint32_t okb = __ballot_sync(0xffffffffu, valid && ((lane & 7) == 7 || s_next == my_src + 1));
+                const bool run8 = ((okb >> (lane & 24)) & 0xffu) == 0xffu;
+                if (run8) {
+                    if ((lane & 7) == 0) {
+                        tma_reduce_add_2d(&tm_dpj8, 32 * half, my_src, B3 + half * 16384 + row * 128);
+                        bulk_commit();
+                    }
+                } else if (valid) {
+                    tma_reduce_add_2d(&tm_dpj, 32 * half, my_src, B3 + half * 16384 + row * 128);
+                    bulk_commit();
+                }
             }
             const int32_t dprev = __shfl_up_sync(0xffffffffu, my_dst, 1);
             const uint32_t sbits = __ballot_sync(0xffffffffu, valid && lane > 0 && my_dst != dprev);
@@ -511,14 +524,14 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
 
 template <bool FIRST, bool NODE, bool X3>
 static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, const CUtensorMap& tde, const CUtensorMap& tout,
-                                 const CUtensorMap& tdpj, const BwdWgArgs& a, int grid, cudaStream_t st) {
+                                 const CUtensorMap& tdpj, const CUtensorMap& tdpj8, const BwdWgArgs& a, int grid, cudaStream_t st) {
     const int smem = (int)sizeof(BwdWgSmem) + 1024;
     static bool done = false;
     if (!done) {
         GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, tdpj, a);
+    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, tdpj, tdpj8, a);
     return GCRL_OK;
 }
 
@@ -553,7 +566,7 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
-    CUtensorMap te, tm, tde, tout, tdpj;
+    CUtensorMap te, tm, tde, tout, tdpj, tdpj8;
     int rc;
     // unused maps point at a valid [N,64] array so that encoding never fails
     if ((rc = make_tmap_rows64(&te, first ? Pi : e_prev, first ? N : E, 128))) return rc;
@@ -561,16 +574,17 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     if ((rc = make_tmap_rows64(&tde, no_de ? Pi : de, no_de ? N : E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tout, first ? Pi : de_prev, first ? N : E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tdpj, dPj, N, 1))) return rc;
+    if ((rc = make_tmap_rows64(&tdpj8, dPj, N, 8))) return rc;
     const int64_t tiles = (E + TILE - 1) / TILE;
     const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
     const int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (no_de ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
-    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
-                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
-    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
-                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
-    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, tdpj, a, (int)grid, st)
-                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, tdpj, a, (int)grid, st);
+    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
+                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
+    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
+                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
+    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
+                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
     prof_end(tok, st);
     if (rc) return rc;
     GCRL_LAUNCH_CHECK();

@@ -4,5 +4,3 @@ import sys,json
 d=json.loads(sys.stdin.read())
 print('$1 DBG=$GCRL_WS_DBG', round(d['value']), round(d['ms_per_step'],1), {k:(round(v['avg_ms'],3), round(v['gbps'])) for k,v in d['kernels'].items() if 'bwd' in k})"; }
 run bf16x3
-GCRL_WS_DBG=16 run bf16x3
-GCRL_WS_DBG=48 run bf16x3
