@@ -289,21 +289,22 @@ def main():
             if k in bytes_per_edge:
                 kernels[k]['gbps'] = bytes_per_edge[k] * E_micro / (avg * 1e-3) / 1e9
     dom = max((k for k in kernels if k in bytes_per_edge), key=lambda k: kernels[k]['share_of_step'])
-    # which kernel serves each launch kind (gn_forward.cu / gn_backward.cu dispatch): the pipelined backward
-    # (k_edge_bwd_ws) for blocks 1-4, the single-group tensor-core kernels elsewhere
+    # which kernel serves each launch kind (gn_forward.cu / gn_backward.cu dispatch): the multi-group kernels
+    # (k_edge_fwd_wg / k_edge_bwd_wg) unless GCRL_FWD_IMPL / GCRL_EDGE_IMPL select an older one
     fwd_impl = {'ws': '_ws', 'tc': '_tc'}.get(os.environ.get('GCRL_FWD_IMPL', '')[:2], '_wg')
-    bwd_impl = '_tc' if os.environ.get('GCRL_EDGE_IMPL', '') == 'tc' else '_ws'
+    bwd_impl = {'ws': '_ws', 'tc': '_tc'}.get(os.environ.get('GCRL_EDGE_IMPL', '')[:2], '_wg')
     if args.math == 'fp32':
         fwd_impl = bwd_impl = ''
     kname = {'edge_fwd_first': 'k_edge_fwd%s<first>' % fwd_impl, 'edge_fwd': 'k_edge_fwd%s' % fwd_impl,
              'edge_fwd_last': 'k_edge_fwd%s<last>' % fwd_impl, 'edge_bwd_first': 'k_edge_bwd%s<first>' % bwd_impl,
              'edge_bwd': 'k_edge_bwd%s' % bwd_impl,
              'edge_bwd_last': 'k_edge_bwd%s<block 5>' % bwd_impl}[dom]
-    # DRAM traffic per launch: bytes per edge of this kernel from the committed `ncu --set full` capture
-    # (profiles/r01_traffic.json, dram__bytes_read.sum + dram__bytes_write.sum over the edges of that launch)
+    # DRAM traffic per launch: bytes per edge of this kernel from the committed ncu capture
+    # (profiles/r01b_traffic.json, dram__bytes_read.sum + dram__bytes_write.sum over the edges of that launch)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_traffic.json')))
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles',
+                                         'r01b_traffic.json' if bwd_impl == '_wg' else 'r01_traffic.json')))
         ent = tj.get(args.math, {}).get(dom)
         if ent:
             traffic = ent['dram_bytes_per_edge'] * E_micro

@@ -25,6 +25,13 @@ namespace gcrl {
 
 using namespace tc;
 
+// phase timeline of group 0 of CTA 0 (diagnostic build: GCRL_NVCC_FLAGS=-DGCRL_FWD_TRACE_BUILD)
+#ifdef GCRL_FWD_TRACE_BUILD
+#define FW_TR(k) do { if (tid == 0 && blockIdx.x == 0) { const long long c_ = clock64(); tr_acc[k] += c_ - tr_last; tr_last = c_; } } while (0)
+#else
+#define FW_TR(k) do { } while (0)
+#endif
+
 constexpr int WG_N = 4;
 constexpr int WG_THREADS = 128 * WG_N;
 
@@ -96,6 +103,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 8; ++c) piv[c] = make_float2(0.f, 0.f);
 
+#ifdef GCRL_FWD_TRACE_BUILD
+    long long tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
+    int tr_tiles = 0;
+#endif
     const int64_t n_items = ((int64_t)a.E + ITEM_EDGES - 1) / ITEM_EDGES;
     for (int64_t it = (int64_t)blockIdx.x * WG_N + wg; it < n_items; it += (int64_t)gridDim.x * WG_N) {
         const int32_t v0 = seg_lower_bound(a.seg_off, a.N, it * ITEM_EDGES);
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
         if (e0 + lt < e1) { nd = __ldg(a.dst + e0 + lt); ns = __ldg(a.src + e0 + lt); }
         for (int32_t t0 = e0; t0 < e1; t0 += TILE) {
             const int nrows = min(TILE, e1 - t0);
+            FW_TR(0);
             dst_s[lt] = nd;
             src_s[lt] = ns;
             named_sync(bar_id, 128);
@@ -170,10 +182,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 tmem_st_16x256b_x8(t_acc1 + ((uint32_t)(32 * w + 16 * g) << 16), v);
             }
             tmem_st_wait();
+            FW_TR(1);
             if (!FIRST) {
                 // ---- e_{l-1}: fp32 landing tile -> bf16 hi/lo operand tile, in place through registers ----------
                 mbar_wait(bar_tma, ph_tma);
                 ph_tma ^= 1;
+                FW_TR(2);
                 float4 x[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -196,6 +210,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             tc_fence_before();
             named_sync(bar_id, 128);
             tc_fence_after();
+            FW_TR(3);
             if (!FIRST) {
                 if (w == 0 && elect_one()) {
                     issue_gemm_feat<X3>(t_acc1, smem_u32(Bh), smem_u32(Bl), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
@@ -205,6 +220,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 ph_mma ^= 1;
                 tc_fence_after();
             }
+            FW_TR(4);
             // ---- hid = relu(acc1) -> operand tile (thread = row, two 32-column halves) ----------------------------
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -221,6 +237,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             fence_proxy_async();
             tc_fence_before();
             named_sync(bar_id, 128);
+            FW_TR(5);
             if (w == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm_feat<X3>(t_acc2, smem_u32(Bh), smem_u32(Bl), smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             mbar_wait(bar_mma, ph_mma);
             ph_mma ^= 1;
             tc_fence_after();
+            FW_TR(6);
             // ---- m = acc2 + b2 -> M (fp32 staging over the operand tile: G2 has finished reading it) ---------------
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -244,6 +262,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             fence_proxy_async();
             tc_fence_before();
             named_sync(bar_id, 128);
+            FW_TR(7);
             // ---- store e_l + segmented PNA reduction -------------------------------------------------------------------
             const bool tma_store = a.m_out && nrows == TILE;
             if (tma_store) {
@@ -263,6 +282,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             }
             tile_reduce_scan_sw_t<ARG>(M, dst_s, S.start_bits[wg], nrows, t0, red, a.out, lt);
             tile_reduce_scan_sw_t<ARG>(M, dst_s, S.start_bits[wg], nrows, t0, red, a.out, lt + 128);
+            FW_TR(8);
             if (tma_store && lt == 0) bulk_wait_read0();
             fence_proxy_async();                   // generic reads of M are ordered before the next TMA load into it
             named_sync(bar_id, 128);
@@ -271,11 +291,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 tma_load_2d(T, &tm_in, 0, t0 + TILE, bar_tma);
                 tma_load_2d(T + 16384, &tm_in, 32, t0 + TILE, bar_tma);
             }
+            FW_TR(9);
             if (lt < 64) tile_reduce_chain_t(nrows, red, carry, a.out, lt);
+            FW_TR(10);
+#ifdef GCRL_FWD_TRACE_BUILD
+            ++tr_tiles;
+#endif
         }
         if (lt < 64) carry_flush_t(carry, a.out, lt);
         named_sync(bar_id, 128);   // reducer scratch quiescent before the next item
     }
+#ifdef GCRL_FWD_TRACE_BUILD
+    if (tid == 0 && blockIdx.x == 0 && tr_tiles > 0)
+        printf("fwd_wg<%d,%d,%d> grp0 %d tiles, cycles/tile: top %lld ids+gather+st %lld waitTMA %lld convert+sync %lld g1 %lld hid+sync %lld g2 %lld m+sync %lld store+scan %lld storewait+sync %lld chain %lld\n",
+               (int)FIRST, (int)X3, (int)ARG, tr_tiles, tr_acc[0] / tr_tiles, tr_acc[1] / tr_tiles, tr_acc[2] / tr_tiles, tr_acc[3] / tr_tiles,
+               tr_acc[4] / tr_tiles, tr_acc[5] / tr_tiles, tr_acc[6] / tr_tiles, tr_acc[7] / tr_tiles, tr_acc[8] / tr_tiles, tr_acc[9] / tr_tiles,
+               tr_acc[10] / tr_tiles);
+#endif
     tc_fence_before();
     __syncthreads();
     if (tid < 32) tmem_dealloc<512>(S.tmem_base);
