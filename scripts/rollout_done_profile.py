@@ -17,7 +17,7 @@ flat = net.flat_params()
 a = env.first_vertices(); env.step(a)
 alive = []
 for s in range(1, nr):
-    alive.append(int((~env.done).sum().item()))
+    alive.append(int((env.done == 0).sum().item()))
     _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
     a = ops.score_argmax(q, env.colour, env.node_off)
     env.step(a)
