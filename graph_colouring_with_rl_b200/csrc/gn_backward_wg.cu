@@ -13,12 +13,16 @@
 //   B1: TMA landing of e_{l-1} (fp32) -> bf16 hi|lo operand in place (G1, G5) -> fp32 staging of d e_{l-1} -> TMA store
 //   B2: TMA landing of d e_l          -> hid operand (G3)                   -> dz1 operand (G5, G6)
 //   B3: TMA landing of e_l            -> dm operand (G3, G4); dm lives in registers while B1 is converted
+//                                     -> fp32 copy of dz1, source of the dPj reduces
 // and one 64-column TMEM accumulator that is in turn acc1 (Pi+Pj preloaded by tcgen05.st, + G1), acc4 (G4) and
 // acc6 (G6), plus the two weight-gradient accumulators kept for the whole kernel: 192 columns per group.
 //   G1  acc += e_{l-1} . C^T  (on top of Pi[dst]+Pj[src])     G4  acc  = dm . W2
 //   G3  accW2 += dm^T . hid                                    G5  accC += dz1^T . e_{l-1}      G6  acc = dz1 . C
-// The next tile's e_l / d e_l / e_{l-1} loads are issued as soon as G3/G4, G5/G6 and the store have released their
-// buffers, so they fly during the rest of the tile; the dPj / dPi reds run while G5/G6 execute.
+// The next tile's d e_l / e_l / e_{l-1} loads are issued as soon as G5/G6, the dPj reduces and the store have released
+// their buffers.  While G5/G6 run: dPj[src] += dz1 goes out as TMA tensor reduces (cp.reduce.async.bulk.tensor, one-row
+// boxes, eight-row boxes for runs of consecutive sources -- LSU reds cost 0.9 ms per launch, these 0.05 ms), dPi[dst] as
+// warp transpose-reduced column sums.  Every endpoint id a thread needs is fetched in one batch at the top of the tile:
+// next to 225 KB of shared memory the L1 keeps nothing, and a load inside a phase costs that phase an L2 round trip.
 #define GCRL_MBAR_TIMEOUT   // counted waits: a protocol bug traps instead of hanging the GPU
 #include "gn_common.cuh"
 #include "ws.cuh"
