@@ -1,7 +1,7 @@
 """Host-side helpers either side of the hot path (SURVEY 8f N3 + N4), with the reference's names
 and return values: stat files (utils.py:58-125), DIMACS `.col` reader (utils.py:243-282,
 447-466), the complete-graph edge encoding (utils.py:296-323), queen graphs
-(construct_queen_graph.py:3-67).  Pure numpy / Python: nothing here touches the device, and
+(construct_queen_graph.py:3-67), Leighton graphs (construct_leighton_graph.py).  Pure numpy / Python: nothing here touches the device, and
 the graphs these functions describe are handed to the kernels as dense adjacency bytes
 (`adjacency_from_*`), never as the O(n^2)-tuple Python structures the reference builds.
 """
@@ -232,3 +232,113 @@ def erdos_renyi_adjacency(n, p, rng):
     """G(n, p) from a numpy Generator: upper-triangular Bernoulli mirrored."""
     up = np.triu(rng.random((n, n)) < p, 1)
     return (up | up.T).astype(np.uint8)
+
+
+# ---- Leighton graphs (construct_leighton_graph.py) -----------------------------------------------------------------
+def _primes_below(limit):
+    sieve = np.ones(limit, dtype=bool)
+    sieve[:2] = False
+    for p in range(2, int(limit ** 0.5) + 1):
+        if sieve[p]:
+            sieve[p * p::p] = False
+    return [int(p) for p in np.nonzero(sieve)[0]]
+
+
+_PRIMES = _primes_below(7920)          # the reference's hard-coded table: the first 1000 primes, 2..7919
+
+
+def get_prime_factors(n):
+    """construct_leighton_graph.py:get_prime_factors (trial division, with multiplicity for 2 only as there)."""
+    factors = []
+    i = 2
+    while n % i == 0:
+        n //= i
+        factors.append(i)
+    i += 1
+    while i * i <= n:
+        if n % i == 0:
+            n //= i
+            factors.append(i)
+        else:
+            i += 2
+    if n > 1:
+        factors.append(n)
+    return factors
+
+
+def generate_leighton_parameters(n, k):
+    """(m, c, a, b) of Leighton's generator with the reference's draws in the reference's order
+    (generate_m, generate_c, generate_a, generate_b): m >> n with hcf(m, n) = k, hcf(c, m) = 1, every prime of m
+    (and 4, if 4 | m) divides a - 1, b[i] = number of (k - i)-cliques."""
+    n_primes = set(get_prime_factors(n))
+    m_factors = get_prime_factors(k)
+    remaining = [p for p in _PRIMES if p not in n_primes]
+    m = k
+    while m < k * n ** 2:
+        p = random.choice(remaining)
+        m_factors.append(p)
+        m *= p
+    remaining_c = [p for p in _PRIMES if p not in set(m_factors)]
+    c = 1
+    while c < 10 * k * n:
+        c *= random.choice(remaining_c)
+    a_minus_1 = 4 if m % 4 == 0 else 1
+    for p in set(m_factors):
+        a_minus_1 *= p
+    while a_minus_1 < 10 * k * n:
+        a_minus_1 *= random.choice(_PRIMES)
+    b = [random.randrange(1, int(n / k) + 1)] + [random.randrange(int(n / (k - i) + 1)) for i in range(1, k - 1)]
+    return m, c, a_minus_1 + 1, b
+
+
+def leighton_edges(n, k, m, c, a, b, X_0):
+    """generate_Xi / generate_Yi / generate_edges: the linear congruential sequence X_i = (a X_{i-1} + c) mod m, Y_i = X_i
+    mod n, consecutive runs of Y as cliques of size k, k-1, ... (b[i] of each).  Returns the list of (min, max) pairs
+    in generation order (duplicates and self pairs included, as in the reference before its set())."""
+    sizes = [len(b) - i + 1 for i in range(len(b))]
+    length = sum(nc * s for nc, s in zip(b, sizes)) + 1
+    xs = [X_0]
+    for _ in range(1, length):
+        xs.append((a * xs[-1] + c) % m)
+    ys = [x % n for x in xs]
+    edges, pos = [], 1
+    for i, nb in enumerate(b):
+        size = k - i
+        for _ in range(nb):
+            vs = ys[pos:pos + size]
+            pos += size
+            for j, v1 in enumerate(vs):
+                for v2 in vs[j + 1:]:
+                    edges.append((min(v1, v2), max(v1, v2)))
+    return edges
+
+
+def generate_leighton_graph(n, k, X_0=None):
+    """construct_leighton_graph.py:generate_leighton_graph -> (edge_list, edge_attr, edge_ind_dict,
+    target_edge_indices); same random draws, same set-iteration order of target_edge_indices."""
+    m, c, a, b = generate_leighton_parameters(n, k)
+    if X_0 is None:
+        X_0 = random.randrange(m)
+    graph_edges = set(leighton_edges(n, k, m, c, a, b, X_0))
+    el = complete_edge_arrays(n)
+    attr = [0] * el.shape[0]
+    ind = _edge_ind_dict(el)
+    for v in range(n):
+        ind.setdefault(v, {})
+    indices = []
+    for v1, v2 in graph_edges:
+        # a clique that draws the same vertex twice yields a self pair; the reference's dict lookup raises KeyError there
+        i1, i2 = ind[int(v1)][int(v2)], ind[int(v2)][int(v1)]
+        attr[i1] = -1
+        indices.append(i1)
+        attr[i2] = -1
+        indices.append(i2)
+    return [tuple(e) for e in el.tolist()], attr, ind, indices
+
+
+def leighton_adjacency(n, k, X_0=None):
+    """Dense adjacency of a Leighton graph (self pairs dropped instead of raising)."""
+    m, c, a, b = generate_leighton_parameters(n, k)
+    if X_0 is None:
+        X_0 = random.randrange(m)
+    return adjacency_from_edges(n, [e for e in leighton_edges(n, k, m, c, a, b, X_0) if e[0] != e[1]])

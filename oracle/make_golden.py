@@ -413,6 +413,16 @@ def stage_hostutils(ref, ds):
             queens.append(dict(seed=seed, n=n, k=k, edge_list=[list(e) for e in el], edge_attr=list(ea), indices=list(idx),
                                after=random.random()))
         out['queens'] = queens
+        import construct_leighton_graph as cl
+        leighton = []
+        for seed, (n, k) in enumerate([(10, 5), (12, 3), (20, 4), (30, 5), (45, 9)]):
+            random.seed(100 + seed)
+            el, ea, ind, idx = cl.generate_leighton_graph(n, k)
+            leighton.append(dict(seed=100 + seed, n=n, k=k, edge_attr=list(ea), indices=list(idx), after=random.random()))
+        random.seed(7)
+        m, c, a, b = cl.generate_parameters(24, 6)
+        out['leighton'] = leighton
+        out['leighton_params'] = dict(seed=7, n=24, k=6, m=m, c=c, a=a, b=b)
         verts, edges = ['a', 'b', 'c', 'd', 'e'], [('a', 'c'), ('e', 'b'), ('c', 'd'), ('d', 'a')]
         el, ea, ind, idx = U.convert_networkx_to_graph(verts, edges)
         out['convert'] = dict(vertices=verts, edges=[list(e) for e in edges], edge_list=[list(e) for e in el],

@@ -56,6 +56,27 @@ def test_queen_graphs_match_reference_including_rng_draws():
         U.generate_queen_graph(10, 3)
 
 
+def test_leighton_graphs_match_reference_including_rng_draws():
+    for g in GOLDEN['leighton']:
+        random.seed(g['seed'])
+        el, ea, ind, idx = U.generate_leighton_graph(g['n'], g['k'])
+        assert list(ea) == g['edge_attr'] and list(idx) == g['indices']      # incl. the reference's set-iteration order
+        assert random.random() == g['after']
+        assert np.asarray(el).tolist() == U.complete_edge_arrays(g['n']).tolist()
+        random.seed(g['seed'])
+        adj = U.leighton_adjacency(g['n'], g['k'])
+        ela = np.asarray(el)
+        assert (-(adj[ela[:, 0], ela[:, 1]].astype(int)) == np.asarray(g['edge_attr'])).all()
+    p = GOLDEN['leighton_params']
+    random.seed(p['seed'])
+    m, c, a, b = U.generate_leighton_parameters(p['n'], p['k'])
+    assert (m, c, a, b) == (p['m'], p['c'], p['a'], p['b'])
+    # Leighton's conditions: hcf(m, n) = k, hcf(c, m) = 1, every prime factor of m divides a - 1
+    from math import gcd
+    assert gcd(m, p['n']) == p['k'] and gcd(c, m) == 1
+    assert all((a - 1) % q == 0 for q in set(U.get_prime_factors(m)))
+
+
 def test_convert_networkx_matches_reference():
     c = GOLDEN['convert']
     el, ea, ind, idx = U.convert_networkx_to_graph(c['vertices'], [tuple(e) for e in c['edges']])
