@@ -56,7 +56,9 @@ class DeviceTrainer(object):
         self.gen.manual_seed(int(device_seed))
         self.memory = DeviceReplayBuffer(buffer_size or agent.max_buffer_size, self.pool)
         kw = {} if max_edges_per_micro_batch is None else dict(max_edges_per_micro_batch=max_edges_per_micro_batch)
-        self.learner = QLearner(agent, process_group=process_group, **kw)
+        # single-GPU loop: without an explicit group the learner stays local even under torchrun (ranks would take
+        # data-dependent numbers of learn steps, so a shared all-reduce cadence needs a design of its own)
+        self.learner = QLearner(agent, process_group=process_group, local_only=process_group is None, **kw)
         self.validate_every = int(validate_every)
         self.out_dir = out_dir
         self.t_step = 0

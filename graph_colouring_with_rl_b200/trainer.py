@@ -79,12 +79,15 @@ class _Slice(object):
 
 
 class QLearner(object):
-    def __init__(self, agent, max_edges_per_micro_batch=512 * 200 * 199, process_group=None):
+    def __init__(self, agent, max_edges_per_micro_batch=512 * 200 * 199, process_group=None, local_only=False):
+        """local_only: never communicate, even inside an initialised process group (a learner that only some ranks
+        run, e.g. the single-GPU training loop, must not enter collectives the other ranks do not)."""
         self.agent = agent
         self.max_edges = int(max_edges_per_micro_batch)
         self.group = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if not local_only and (process_group is not None or
+                               (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self._stash = None
 

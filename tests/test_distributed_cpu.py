@@ -43,6 +43,10 @@ def _worker(rank, world, port, out_dir):
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     torch.set_num_threads(2)
+    # a learner only some ranks run (the single-GPU training loop, bench.py's train_loop extra on rank 0) must not
+    # pick up the default process group: it would enter all-reduces the other ranks never post
+    from graph_colouring_with_rl_b200.trainer import QLearner
+    assert QLearner(object()).world == world and QLearner(object(), local_only=True).world == 1
     params = util.load_parity_weights()
     obs, actions, targets = _make_batch()
     lo, hi = shard_range(len(obs), rank, world)
