@@ -137,6 +137,29 @@ def oracle_fwd_bwd_graphs_per_sec(n, sample_graphs, iters, seed=1):
     return sample_graphs / float(np.mean(times)), cores, times
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    communicator, the agent prints 'Starting learning' like the reference): send fd 1 to stderr for the whole run and keep
+    the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (the oracle port; the
     reference itself needs torch_geometric/torch_scatter/gym, absent on the box) on host cores."""
@@ -157,7 +180,7 @@ def run_reference(args, rank):
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -178,6 +201,7 @@ def main():
     ap.add_argument('--skip-extras', action='store_true', help='only the headline metric')
     args = ap.parse_args()
 
+    capture_stdout()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -349,7 +373,7 @@ def main():
                                     'sample': '%d ER(0.5) graphs x %d vertices, oracle/gn_oracle.py fwd+bwd (reference op order, '
                                               'torch CPU, %d threads), mean of 3 after 1 warm-up' % (args.cpu_sample_graphs, n, cores)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
