@@ -16,7 +16,7 @@
 //   * groups synchronise with named barriers and their own mbarriers only, so one group's MMA / TMA / gather
 //     latency is covered by the other three.
 // TMEM: 128 columns per group (acc1, acc2) = all 512.  Shared memory: 32 + 4 x (32 + 12) + ids = 214 KB.
-#define GCRL_MBAR_TIMEOUT   // counted waits: a protocol bug traps instead of hanging the GPU
+#define GCRL_MBAR_TIMEOUT   // counted waits (a protocol bug traps instead of hanging the GPU): measurably faster here than the tight loop (3.27 vs 3.49 ms)
 #include "gn_common.cuh"
 #include "ws.cuh"
 #include <stdlib.h>
