@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- generate tests/golden/* by running the UNMODIFIED reference
 (/root/reference, imported through oracle/ref_import.py) in this container.
 
-    python -m oracle.make_golden [stage ...]      stages: graphs env train forward learn rollouts trainloop hostutils
+    python -m oracle.make_golden [stage ...]      stages: graphs env train forward learn rollouts trainloop hostutils replay
 
 The fixtures are what travels to the GPU box (where /root/reference does not exist); every
 fixture records the script stage and seeds that produced it.
@@ -441,6 +441,53 @@ def stage_hostutils(ref, ds):
     with open(os.path.join(GOLD, 'host_utils.json'), 'w') as f:
         json.dump(out, f)
     print('hostutils: wrote', os.path.getsize(os.path.join(GOLD, 'host_utils.json')), 'bytes')
+
+
+def stage_replay(ref, ds):
+    """The reference ReplayBuffer (dqn_agent.py:8-65) with 11 slots fed 29 env transitions (the ring wraps twice), then
+    three seeded sample_buffer calls: what each minibatch returned (colours before / after, actions, rewards, dones,
+    assigned one-hots, batched edge_attr checksum).  Pins oracle/replay_oracle.py."""
+    import gym
+    rng = random.Random(17)
+    env = gym.make('graph-colouring-v0', dataset_graphs=ds.graphs)
+    mem = ref.dqn_agent.ReplayBuffer(11, 0)
+    gids, cur_c, nxt_c, acts, rews, dones = [], [], [], [], [], []
+    gi_list = [2, 31, 64, 77]
+    k = 0
+    while k < 29:
+        gi = gi_list[k % len(gi_list)]
+        t = ds.graphs[gi]
+        _, cur = env.reset(target=t)
+        data, gf = env.GenerateData_v1(t, cur)
+        done = False
+        while not done and k < 29:
+            v = rng.choice(cur['unassigned_vertices'])
+            nxt, r, done, info = env.step(v)
+            ndata, ngf = env.GenerateData_v1(t, nxt)
+            mem.store_transition(data, gf, np.array(nxt['assigned_vertices_onehot']), v, r, ndata, ngf, int(done))
+            gids.append(gi)
+            cur_c.append(data.x[:, 1].numpy().astype(np.int16))
+            nxt_c.append(ndata.x[:, 1].numpy().astype(np.int16))
+            acts.append(int(v)); rews.append(float(r)); dones.append(int(done))
+            data, gf, cur = ndata, ngf, nxt
+            k += 1
+    out = dict(capacity=np.asarray(11), graph_ids=np.asarray(gids, dtype=np.int32), cur=np.concatenate(cur_c),
+               nxt=np.concatenate(nxt_c), actions=np.asarray(acts, dtype=np.int32), rewards=np.asarray(rews, dtype=np.float32),
+               dones=np.asarray(dones, dtype=np.int32), count=np.asarray(mem.current_mem_size))
+    np.random.seed(23)
+    for b in range(3):
+        d, gfs, assigned, a, r, nd, ngfs, dn = mem.sample_buffer(6)
+        out['s%d_x' % b] = d.x[:, 1].numpy().astype(np.int16)
+        out['s%d_nx' % b] = nd.x[:, 1].numpy().astype(np.int16)
+        out['s%d_nodes' % b] = np.asarray([int(n) for n in np.bincount(d.batch.numpy())], dtype=np.int32)
+        out['s%d_actions' % b] = a.reshape(-1).astype(np.int32)
+        out['s%d_rewards' % b] = r.astype(np.float32)
+        out['s%d_dones' % b] = dn.astype(np.int32)
+        out['s%d_assigned' % b] = np.concatenate([np.asarray(x) for x in assigned]).astype(np.int8)
+        out['s%d_present_edges' % b] = np.asarray(int((d.edge_attr == -1).sum()))
+    out['provenance'] = np.asarray('oracle/make_golden.py stage_replay: reference ReplayBuffer(11, 0), 29 transitions, np.random.seed(23), 3 x sample_buffer(6)')
+    np.savez_compressed(os.path.join(GOLD, 'replay_buffer.npz'), **out)
+    print('replay: stored', mem.current_mem_size)
 
 
 def main(argv):

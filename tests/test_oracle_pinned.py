@@ -138,3 +138,29 @@ def test_rollouts_match_reference():
         if gaps[gi].size == 0 or gaps[gi].min() > 1e-5:
             assert seq == [int(v) for v in seqs[gi]], g['name']
             assert used == int(d['colours_used'][gi])
+
+
+def test_replay_oracle_matches_reference_replay_buffer():
+    """oracle/replay_oracle.py against the reference ReplayBuffer (tests/golden/replay_buffer.npz): ring index, wrap-around
+    and the minibatches three seeded sample_buffer calls returned."""
+    from oracle.replay_oracle import ReplayOracle
+    d = np.load(os.path.join(util.GOLD, 'replay_buffer.npz'))
+    graphs = util.load_validation_graphs()
+    cap = int(d['capacity'])
+    orc = ReplayOracle(cap, [g['adj'] for g in graphs])
+    ns = [graphs[int(g)]['n'] for g in d['graph_ids']]
+    cur, nxt = util.split_by(d['cur'], ns), util.split_by(d['nxt'], ns)
+    for i, g in enumerate(d['graph_ids']):
+        slot = orc.store(int(g), cur[i], nxt[i], d['actions'][i], d['rewards'][i], d['dones'][i])
+        assert slot == i % cap                                              # dqn_agent.py:33
+    assert orc.count == int(d['count'])
+    np.random.seed(23)
+    for b in range(3):
+        idx = np.random.choice(min(orc.count, cap), 6)                      # dqn_agent.py:47-48
+        out = orc.gather(idx)
+        assert np.array_equal(out['ns'], d['s%d_nodes' % b])
+        assert np.array_equal(out['cur_colour'], d['s%d_x' % b]) and np.array_equal(out['next_colour'], d['s%d_nx' % b])
+        assert np.array_equal(out['action'], d['s%d_actions' % b]) and np.array_equal(out['done'], d['s%d_dones' % b])
+        assert np.array_equal(out['reward'], d['s%d_rewards' % b])
+        assert np.array_equal((out['next_colour'] >= 0).astype(np.int8), d['s%d_assigned' % b])
+        assert int(out['adj'].sum()) == int(d['s%d_present_edges' % b])     # both directions of every edge, like edge_attr == -1

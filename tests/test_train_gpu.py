@@ -87,6 +87,38 @@ def test_replay_ring_store_gather_bit_exact_with_wraparound():
     assert np.array_equal(idx, np.random.choice(97, 16))               # dqn_agent.py:47-48
 
 
+def test_device_ring_reproduces_reference_replay_buffer_golden():
+    """The reference ReplayBuffer's own run (tests/golden/replay_buffer.npz: 29 transitions into 11 slots, three seeded
+    sample_buffer calls) through gcrl_replay_store / gcrl_replay_gather."""
+    from graph_colouring_with_rl_b200.envs import BatchedColouringEnv
+    from graph_colouring_with_rl_b200.replay import DeviceReplayBuffer, GraphPool
+    d = np.load(util.GOLD + '/replay_buffer.npz')
+    pool = GraphPool([g['adj'] for g in GRAPHS])
+    buf = DeviceReplayBuffer(int(d['capacity']), pool)
+    ns = [GRAPHS[int(g)]['n'] for g in d['graph_ids']]
+    cur, nxt = util.split_by(d['cur'], ns), util.split_by(d['nxt'], ns)
+    dev = pool.device
+    for i, g in enumerate(d['graph_ids']):
+        env = BatchedColouringEnv.from_pool(pool, [int(g)])
+        env.colour.copy_(torch.from_numpy(nxt[i].astype(np.int32)).to(dev))
+        env.reward.fill_(float(d['rewards'][i]))
+        env.done.fill_(int(d['dones'][i]))
+        buf.store_from_env(env, [int(g)], torch.from_numpy(cur[i].astype(np.int32)).to(dev),
+                           torch.tensor([int(d['actions'][i])], dtype=torch.int32, device=dev))
+    assert buf.current_mem_size == int(d['count'])
+    np.random.seed(23)
+    for b in range(3):
+        tb = buf.sample_buffer(6)                                            # np.random.choice like dqn_agent.py:47-48
+        buf.check()
+        assert np.array_equal(tb.ns, d['s%d_nodes' % b])
+        assert np.array_equal(tb.cur_colour.cpu().numpy(), d['s%d_x' % b])
+        assert np.array_equal(tb.next_colour.cpu().numpy(), d['s%d_nx' % b])
+        assert np.array_equal(tb.action.cpu().numpy(), d['s%d_actions' % b])
+        assert np.array_equal(tb.reward.cpu().numpy(), d['s%d_rewards' % b])
+        assert np.array_equal(tb.done.cpu().numpy(), d['s%d_dones' % b])
+        assert int(tb.adj.sum().item()) == int(d['s%d_present_edges' % b])
+
+
 def test_replay_gather_vector_path_and_padding():
     # vertex counts that are multiples of 4 keep every adjacency block 16-byte aligned (uint4 copies);
     # a stride larger than the largest graph exercises the -1 padding
