@@ -144,7 +144,7 @@ def test_replay_oracle_matches_reference_replay_buffer():
     """oracle/replay_oracle.py against the reference ReplayBuffer (tests/golden/replay_buffer.npz): ring index, wrap-around
     and the minibatches three seeded sample_buffer calls returned."""
     from oracle.replay_oracle import ReplayOracle
-    d = np.load(os.path.join(util.GOLD, 'replay_buffer.npz'))
+    d = np.load(util.GOLD + '/replay_buffer.npz')
     graphs = util.load_validation_graphs()
     cap = int(d['capacity'])
     orc = ReplayOracle(cap, [g['adj'] for g in graphs])
