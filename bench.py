@@ -368,6 +368,7 @@ def main():
         if rank == 0:
             line['rollouts'] = line_roll
             line['train_loop'] = bench_train_loop(dev, args)
+            line['large_graphs'] = bench_large_graphs(agent, dev)
             v, cores, times = oracle_fwd_bwd_graphs_per_sec(n, args.cpu_sample_graphs, 3)
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                     'sample': '%d ER(0.5) graphs x %d vertices, oracle/gn_oracle.py fwd+bwd (reference op order, '
@@ -442,6 +443,39 @@ def bench_pna(lib, ops, dev, hbm_peak, peak_src, args):
     return {'workload': '%d graphs x %d vertices, one block: msg [%d,64] fp32' % (Gr, nr, E), 'avg_ms': avg,
             'algorithmic_bytes': nbytes, 'achieved': gbps, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbps / hbm_peak,
             'peak_source': peak_src, 'l2': 'input 6.3 GB >> L2'}
+
+
+def bench_large_graphs(agent, dev):
+    """Larger-graph inference (BASELINE.json configs[3]): one action-scoring step (Q of every vertex + masked argmax) on a
+    single ER(0.5) graph of 100-1000 vertices (up to 999 000 complete-graph edges), and on a batch of 32 x 250 vertices."""
+    import torch
+    from graph_colouring_with_rl_b200 import ops
+    from graph_colouring_with_rl_b200.envs import BatchedColouringEnv
+    from graph_colouring_with_rl_b200.utils import erdos_renyi_adjacency
+    net = agent.gn_behaviour
+    flat = net.flat_params()
+    rng = np.random.default_rng(3)
+    out = {}
+    for tag, n, B in (('n100', 100, 1), ('n250', 250, 1), ('n500', 500, 1), ('n1000', 1000, 1), ('32xn250', 250, 32)):
+        env = BatchedColouringEnv([erdos_renyi_adjacency(n, 0.5, rng) for _ in range(B)], device=dev)
+        packed, eattr = env.packed
+        env.step(env.first_vertices())
+
+        def step():
+            _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
+            return ops.score_argmax(q, env.colour, env.node_off)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        out[tag] = {'ms_per_scoring_step': a.elapsed_time(b) / 20, 'edges': int(env.n_edges)}
+    out['workload'] = 'Q of every vertex + masked argmax per call, ER(0.5), mean of 20 calls after 3 warm-ups'
+    return out
 
 
 def bench_rollouts(agent, dev, args, rank, world, max_over_ranks, barrier):
