@@ -57,6 +57,7 @@ struct FwdWgArgs {
     int32_t N, E;
     float* m_out;
     AggOut out;
+    int item_edges;                           // target edges per work item (an item is a run of whole segments)
 };
 
 template <bool FIRST, bool X3, bool ARG>
@@ -107,10 +108,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
     long long tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last = clock64();
     int tr_tiles = 0;
 #endif
-    const int64_t n_items = ((int64_t)a.E + ITEM_EDGES - 1) / ITEM_EDGES;
+    const int64_t IE = a.item_edges;
+    const int64_t n_items = ((int64_t)a.E + IE - 1) / IE;
     for (int64_t it = (int64_t)blockIdx.x * WG_N + wg; it < n_items; it += (int64_t)gridDim.x * WG_N) {
-        const int32_t v0 = seg_lower_bound(a.seg_off, a.N, it * ITEM_EDGES);
-        const int32_t v1 = (it + 1 == n_items) ? a.N : seg_lower_bound(a.seg_off, a.N, (it + 1) * ITEM_EDGES);
+        const int32_t v0 = seg_lower_bound(a.seg_off, a.N, it * IE);
+        const int32_t v1 = (it + 1 == n_items) ? a.N : seg_lower_bound(a.seg_off, a.N, (it + 1) * IE);
         const int32_t e0 = a.seg_off[v0], e1 = a.seg_off[v1];
         Carry carry;
         carry.dst = -1;
@@ -355,7 +357,16 @@ int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, co
     if (rc) return rc;
     rc = make_tmap_rows64(&tout, m_out ? m_out : Pi, m_out ? E : N, 128);
     if (rc) return rc;
-    const int64_t items = (E + ITEM_EDGES - 1) / ITEM_EDGES;
+    // Work items are runs of whole segments of about item_edges edges, one warp group walks an item tile by tile.  Large
+    // batches: ITEM_EDGES (16 tiles).  Small ones (a 64-graph replay minibatch is 70 k edges = 34 such items for 592 warp
+    // groups: the launch took 0.22 ms, one group's serial time): shrink the items until every group has one.
+    {
+        const int64_t groups = (int64_t)sm_count() * WG_N;
+        int64_t ie = (E + groups - 1) / groups;
+        ie = (ie + TILE - 1) / TILE * TILE;
+        a.item_edges = (int)(ie < TILE ? TILE : (ie > ITEM_EDGES ? ITEM_EDGES : ie));
+    }
+    const int64_t items = (E + a.item_edges - 1) / a.item_edges;
     int64_t grid = sm_count();
     if (grid > (items + WG_N - 1) / WG_N) grid = (items + WG_N - 1) / WG_N;
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_FWD_FIRST : (m_out ? GCRL_PROF_EDGE_FWD : GCRL_PROF_EDGE_FWD_LAST), st);
