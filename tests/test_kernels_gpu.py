@@ -182,6 +182,40 @@ def test_gn_forward_tensor_core_modes(weights, math_mode):
     assert a.shape == b.shape
 
 
+@pytest.mark.parametrize('math_mode,tol', [(0, 2e-5), (2, 3e-4), (1, 6e-2)])
+def test_tiny_and_ragged_graphs_forward_backward(math_mode, tol):
+    """Edge cases of the segment layout: a batch mixing an isolated vertex (no edges: empty segment, every aggregator 0,
+    std = sqrt(1e-5)), graphs of 2, 3 and 5 vertices (segments of 1, 2 and 4 rows: many segments per 32-row quarter) and a
+    dataset graph, so one 128-row tile holds dozens of segment boundaries; then two-edge and eight-edge batches (a lone
+    isolated vertex is not a reference case: its aggregate() sizes the output by index.max() + 1 and fails on no edges)."""
+    rng = np.random.default_rng(21)
+    params = util.load_parity_weights()
+
+    def obs_of(n, frac):
+        adj = np.ones((n, n), dtype=np.uint8) - np.eye(n, dtype=np.uint8)
+        if n > 3:
+            adj[0, 1] = adj[1, 0] = 0
+        return gn_oracle.observation(adj, util.random_colours(n, adj, frac, rng))
+    g = GRAPHS[17]
+    batches = [[obs_of(1, 0), obs_of(2, 0), obs_of(3, .4), obs_of(5, .4), obs_of(2, .5), obs_of(1, 0), obs_of(4, .3),
+                gn_oracle.observation(g['adj'], util.random_colours(g['n'], g['adj'], .4, rng), g['edge_list'])],
+               [obs_of(2, 0)], [obs_of(1, 0), obs_of(3, 0)]]
+    for obs in batches:
+        x, ei, ea = gn_oracle.collate(obs)
+        N = x.shape[0]
+        with torch.no_grad():
+            h_ref, q_ref = gn_oracle.gn_forward(params, x, ei, ea)
+        flat, P, ea_i, h, q, st = run_forward(params, x, ei, ea, stash=True, math_mode=math_mode)
+        assert float((q.cpu() - q_ref.view(-1)).abs().max()) <= tol, (math_mode, N)
+        torch.manual_seed(3)
+        d_q = torch.randn(N)
+        got = ops().gn_backward(flat, (2, 1, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), math_mode=math_mode).cpu().numpy()
+        truth = oracle_grads(params, x, ei, ea, d_q, None, torch.float64)
+        assert np.all(np.isfinite(got))
+        rel = float(np.linalg.norm(got - truth) / max(np.linalg.norm(truth), 1e-30))
+        assert rel <= {0: 1e-3, 2: 5e-3, 1: 0.3}[math_mode], (math_mode, N, rel)
+
+
 @pytest.mark.parametrize('weights', ['init', 'trained'])
 def test_gn_forward_vs_oracle(weights):
     rng = np.random.default_rng(4)
