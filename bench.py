@@ -361,12 +361,15 @@ def main():
         learner._stash = None
         _lib._ws_cache.clear()
         torch.cuda.empty_cache()
-        extras_ok = rank == 0
-        if extras_ok:
+        # single-GPU side measurements and the CPU baseline: at N = 1 only (at N > 1 the other ranks would idle at the
+        # final barrier while rank 0 runs them)
+        single = rank == 0 and world == 1
+        if single:
             line['pna'] = bench_pna(lib, ops, dev, hbm_peak, peak_src, args)
         line_roll = bench_rollouts(agent, dev, args, rank, world, max_over_ranks, barrier)
         if rank == 0:
             line['rollouts'] = line_roll
+        if single:
             line['train_loop'] = bench_train_loop(dev, args)
             line['large_graphs'] = bench_large_graphs(agent, dev)
             v, cores, times = oracle_fwd_bwd_graphs_per_sec(n, args.cpu_sample_graphs, 3)
