@@ -53,7 +53,7 @@ SIGNATURES = {
     'gcrl_gn_backward': (c_int, [P, c_int, c_int, c_int, c_int64, c_int64, P, P, P, P, P, P, P, P, P, P,
                                  P, c_int, P, c_size_t, c_int, P]),
     'gcrl_score_argmax': (c_int, [P, P, P, c_int32, P, P, P]),
-    'gcrl_td_target_loss': (c_int, [P, P, P, P, c_int32, P, P, P, c_float, c_int32, P, P, P, P, P]),
+    'gcrl_td_target_loss': (c_int, [P, P, P, P, c_int32, P, P, P, c_float, c_int32, P, P, P, P, P, P]),
     'gcrl_adam_soft_update': (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float,
                                       c_int64, c_float, P]),
     'gcrl_soft_update': (c_int, [P, P, c_int64, c_float, P]),

@@ -37,11 +37,27 @@ def _device():
 class _PackCache(object):
     """Segment layouts keyed by the identity of the caller's edge_index tensor: the environment
     hands out the same static edge_index every step of an episode (graph_colouring_env.py:136),
-    so batching is done once per graph, not once per step."""
+    so batching is done once per graph, not once per step.
 
-    def __init__(self, capacity=256):
+    Bounded by BYTES (layout + permuted edge_attr + the key tensors it keeps alive), default 256 MB, and
+    single inputs larger than a quarter of the budget are not cached at all: a caller that builds a fresh
+    `Batch.from_data_list(...)` per learn() never hits the cache and must not pin a minibatch per entry.
+    The key includes the tensors' `_version`; writes that bypass it (`.data`, raw-pointer kernels) are not
+    seen -- do not mutate a cached edge_index / edge_attr in place, or call `clear_pack_cache()`."""
+
+    def __init__(self, capacity=256, max_bytes=256 << 20):
         self.capacity = capacity
+        self.max_bytes = int(max_bytes)
+        self.bytes = 0
         self.items = OrderedDict()
+
+    @staticmethod
+    def _nbytes(*tensors):
+        return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+    def clear(self):
+        self.items.clear()
+        self.bytes = 0
 
     def get(self, edge_index, n_vertices, edge_attr):
         key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(n_vertices),
@@ -52,14 +68,24 @@ class _PackCache(object):
             return hit[0], hit[1]
         packed = ops.pack(edge_index, n_vertices)
         eattr_i = ops.permute_rows(edge_attr.reshape(edge_attr.shape[0], -1), packed.perm, True)
+        nb = self._nbytes(packed.seg_off, packed.src, packed.dst, packed.perm, eattr_i, edge_index, edge_attr)
+        if nb > self.max_bytes // 4:
+            return packed, eattr_i
         # keep the key tensors alive so their addresses cannot be recycled while cached
-        self.items[key] = (packed, eattr_i, edge_index, edge_attr)
-        if len(self.items) > self.capacity:
-            self.items.popitem(last=False)
+        self.items[key] = (packed, eattr_i, edge_index, edge_attr, nb)
+        self.bytes += nb
+        while len(self.items) > self.capacity or self.bytes > self.max_bytes:
+            _, old = self.items.popitem(last=False)
+            self.bytes -= old[4]
         return packed, eattr_i
 
 
 _pack_cache = _PackCache()
+
+
+def clear_pack_cache():
+    """Drop every cached segment layout (after mutating an edge_index / edge_attr in place, or to free memory)."""
+    _pack_cache.clear()
 
 
 def _mlp(in_dim, hidden_dim, out_dim):

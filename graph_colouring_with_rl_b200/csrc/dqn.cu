@@ -50,7 +50,7 @@ __global__ void k_td_target_loss(const float* __restrict__ q_cur, const float* _
                                  const int32_t* __restrict__ action, const float* __restrict__ reward,
                                  const int32_t* __restrict__ done, float gamma, float inv_b,
                                  float* __restrict__ q_expected, float* __restrict__ q_target,
-                                 float* __restrict__ d_q, float* __restrict__ loss) {
+                                 float* __restrict__ d_q, float* __restrict__ loss, int32_t* __restrict__ err) {
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -62,14 +62,21 @@ __global__ void k_td_target_loss(const float* __restrict__ q_cur, const float* _
         for (int32_t i = lane; i < n; i += 32) d_q[v0 + i] = 0.f;
         __syncwarp();
         if (lane == 0) {
+            const int32_t act = action[g];
+            if (act < 0 || act >= n) {            // a bad / sentinel action: no contribution, no out-of-bounds access
+                if (err) atomicCAS(err, 0, (int32_t)(g + 1));
+                if (q_expected) q_expected[g] = NAN;
+                if (q_target) q_target[g] = NAN;
+                continue;
+            }
             const int32_t dn = done[g];
             float qn = (dn == 1) ? 0.f : best;                              // :207
             const float tgt = reward[g] + (gamma * qn) * (float)(1 - dn);   // :212
-            const float qe = q_cur[v0 + action[g]];                         // :178-184
+            const float qe = q_cur[v0 + act];                         // :178-184
             const float diff = qe - tgt;
             if (q_expected) q_expected[g] = qe;
             if (q_target) q_target[g] = tgt;
-            d_q[v0 + action[g]] = 2.f * diff * inv_b;                       // d mse / d q
+            d_q[v0 + act] = 2.f * diff * inv_b;                       // d mse / d q
             atomicAdd(loss, diff * diff * inv_b);                           // :215 (mean)
         }
     }
@@ -139,13 +146,13 @@ int gcrl_score_argmax(const float* q, const int32_t* colour, const int32_t* node
 int gcrl_td_target_loss(const float* q_cur, const float* q_next, const int32_t* next_colour,
                         const int32_t* node_off, int32_t G, const int32_t* action,
                         const float* reward, const int32_t* done, float gamma, int32_t batch_total,
-                        float* q_expected, float* q_target, float* d_q, float* loss, void* stream) {
+                        float* q_expected, float* q_target, float* d_q, float* loss, int32_t* err, void* stream) {
     GCRL_CHECK_ARG(G >= 0 && batch_total >= 1);
     if (G == 0) return GCRL_OK;
     GCRL_CHECK_ARG(q_cur && q_next && next_colour && node_off && action && reward && done && d_q && loss);
     k_td_target_loss<<<warp_grid(G), 256, 0, (cudaStream_t)stream>>>(
         q_cur, q_next, next_colour, node_off, G, action, reward, done, gamma, 1.0f / (float)batch_total,
-        q_expected, q_target, d_q, loss);
+        q_expected, q_target, d_q, loss, err);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -512,30 +512,15 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
     return GCRL_OK;
 }
 
-// gn_backward_tc.cu
+// gn_backward_wg.cu: PNA backward coefficients and the two-group tensor-core edge backward
 int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
                         float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
                         float* gb2_vertex, cudaStream_t st);
-int launch_edge_bwd_tc(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
-                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
-                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
-                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
-                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
-// gn_backward_ws.cu (warp-specialised pipeline; default)
-int launch_edge_bwd_ws(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
-                       const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
-                       const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
-                       const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
-                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
-// GCRL_EDGE_IMPL=tc selects the older single-group tensor-core kernels (A/B comparisons)
-bool use_ws_kernels();
-// gn_backward_wg.cu (two independent tile chains per SM; default.  GCRL_EDGE_IMPL=ws selects the pipeline above)
 int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
-int bwd_impl();
 // gn_node_tc.cu: vertex-side products on the tensor cores
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
                int accumulate, int64_t N, cudaStream_t st);
@@ -665,20 +650,15 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         float* de_prev = (l > 0) ? deb[l & 1] : nullptr;
         const bool tc_ok = (l == 0) ? (b.De <= 8) : (b.De == 64);
         if (E > 0 && math_mode != GCRL_MATH_FP32 && tc_ok) {
-            // the pipelined kernel takes the arg-min/max terms pre-added to d e_l (a workspace buffer
-            // nobody else reads); block 5 has no d e_l and applies them itself
-            // block 5 (e_5 recomputed in-kernel: a longer per-tile chain) is still faster on the single-group kernel
-            // block 5 has no d e_5: with e_5 stashed by the forward it runs as a regular pipelined block (dm without the
-            // d e_l term); GCRL_EDGE_IMPL=tc recomputes e_5 in the single-group kernel instead
-            const bool ws = use_ws_kernels();
-            float* de_scatter = (ws && de_cur) ? const_cast<float*>(de_cur) : nullptr;
-            float* gb2_vertex = nullptr;
+            // the arg-min/max terms are pre-added to d e_l by k_pna_bwd_coef (a workspace buffer nobody else reads: two
+            // scattered reds per (vertex, column) instead of two compares per element); block 5 has no d e_l and applies
+            // them in its dm loop.  The forward stashed e_5, so block 5 runs as a regular block without the d e_l term.
+            float* de_scatter = de_cur ? const_cast<float*>(de_cur) : nullptr;
             RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
-                                   gb2_vertex, st));
-            RC((ws ? (bwd_impl() == 0 ? launch_edge_bwd_wg : launch_edge_bwd_ws) : launch_edge_bwd_tc)(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
-                                  b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E,
-                                  (l == GCRL_N_BLOCKS - 1 && !ws) ? nullptr : S.e[l], de_cur, coef_a, coef_b, dagg, S.amin[l],
-                                  S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
+                                   nullptr, st));
+            RC(launch_edge_bwd_wg(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
+                                  b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E, S.e[l], de_cur, coef_a, coef_b,
+                                  dagg, S.amin[l], S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
         } else if (E > 0) {
             EdgeBwdArgs a;
             a.Pi = S.Pi[l]; a.Pj = S.Pj[l];

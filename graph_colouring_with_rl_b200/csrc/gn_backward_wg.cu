@@ -1,7 +1,7 @@
 // gn_backward_wg.cu -- fused edge kernel of the GN backward pass, two independent tile chains per SM.
 //
-// Same math as k_edge_bwd_ws (gn_backward_ws.cu; reference: loss.backward() through architecture.py:51-66,
-// dqn_agent.py:219).  That kernel is a warp-specialised pipeline whose stages hand ONE tile chain
+// Reference: loss.backward() through architecture.py:51-66 (dqn_agent.py:219).  Round 1 went through two earlier
+// designs (removed; git history): a single-group kernel and a warp-specialised pipeline whose stages hand ONE tile chain
 //   ep1 (hid) -> G3/G4 -> ep3 (dz1) -> G5/G6
 // from role to role; shared memory (224 KB) leaves no room to double-buffer hid/dz1 and dm, so consecutive tiles'
 // chains cannot overlap and the kernel's time is the chain's latency (5.4 ms of its 8.0 ms per launch with every
@@ -43,6 +43,60 @@ using namespace tc;
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, int c0, int c1, const void* smem_src) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(m), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+
+// ca = g_mean/deg - [var>0] g_std * mean / (deg * std),  cb = [var>0] g_std / (deg * std)
+// With de_scatter != null the min / max gradient terms are added to d e_l here (two scattered reds per
+// (vertex, column): 1/(n-1) of the elements) so that the edge kernel's dm pass is purely dense:
+//   d e_l[argmin[v,c], c] += g_min[v,c],  d e_l[argmax[v,c], c] += g_max[v,c].
+__global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __restrict__ agg,
+                               const float* __restrict__ var, const int32_t* __restrict__ seg_off, int64_t N,
+                               float* __restrict__ ca, float* __restrict__ cb, const int32_t* __restrict__ amin,
+                               const int32_t* __restrict__ amax, float* __restrict__ de_scatter,
+                               float* __restrict__ gb2_vertex) {
+    // gb2_vertex != null (block 5, pipelined kernel): db2 = sum over edges of dm = sum_v (g_mean + g_min + g_max)
+    // (the std term sums to zero over a segment), accumulated here instead of in the edge kernel
+    float bacc = 0.f;
+    const int64_t total = N * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = t >> 6;
+        const int c = (int)(t & 63);
+        const float deg = (float)(seg_off[v + 1] - seg_off[v]);
+        float a = 0.f, b = 0.f;
+        if (deg > 0.f) {
+            a = dagg[v * 256 + c] / deg;
+            if (var[t] > 0.f) {
+                b = dagg[v * 256 + 192 + c] / (deg * agg[v * 256 + 192 + c]);
+                a -= b * agg[v * 256 + c];
+            }
+        }
+        ca[t] = a;
+        cb[t] = b;
+        if (gb2_vertex && deg > 0.f) bacc += dagg[v * 256 + c] + dagg[v * 256 + 64 + c] + dagg[v * 256 + 128 + c];
+        if (de_scatter && deg > 0.f) {
+            atomicAdd(de_scatter + (int64_t)amin[t] * 64 + c, dagg[v * 256 + 64 + c]);
+            atomicAdd(de_scatter + (int64_t)amax[t] * 64 + c, dagg[v * 256 + 128 + c]);
+        }
+    }
+    if (gb2_vertex) {       // blockDim = 256 and a grid stride that is a multiple of 64: a thread's column is fixed
+        __shared__ float red[256];
+        red[threadIdx.x] = bacc;
+        __syncthreads();
+        if (threadIdx.x < 64)
+            atomicAdd(&gb2_vertex[threadIdx.x], red[threadIdx.x] + red[threadIdx.x + 64] + red[threadIdx.x + 128] + red[threadIdx.x + 192]);
+    }
+}
+
+int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
+                        float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
+                        float* gb2_vertex, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    int64_t blocks = (N * 64 + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k_pna_bwd_coef<<<(int)blocks, 256, 0, st>>>(dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
 }
 
 constexpr int BG_N = 2;                  // groups per CTA
@@ -539,20 +593,8 @@ static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, c
     return GCRL_OK;
 }
 
-// GCRL_EDGE_IMPL: "wg" this kernel, "ws" the warp-specialised pipeline, "tc" the single-group kernel
-int bwd_impl() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GCRL_EDGE_IMPL");
-        v = 0;
-        if (e && e[0] == 'w' && e[1] == 's') v = 1;
-        if (e && e[0] == 't' && e[1] == 'c') v = 2;
-    }
-    return v;
-}
-
-// Two-group tensor-core edge backward of one block; same contract as launch_edge_bwd_ws (m must be given: the
-// recompute flavour of block 5 stays on the other kernels).
+// Two-group tensor-core edge backward of one block.  m = e_l must be given (the forward stashes e_5 in the tensor-core
+// modes, so block 5 is a regular block without a d e_l term); de == nullptr <=> block 5.
 int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,

@@ -406,23 +406,10 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
     return GCRL_OK;
 }
 
-// gn_forward_tc.cu
-int launch_edge_fwd_tc(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
-                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
-                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
-
-// gn_forward_ws.cu (warp-specialised pipeline; default, GCRL_EDGE_IMPL=tc selects the single-group kernel)
-int launch_edge_fwd_ws(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
-                       const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
-                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
-bool use_ws_kernels();
-bool use_ws_forward();
-
-// gn_forward_wg.cu (four warp groups per SM: the default; GCRL_FWD_IMPL=tc / ws select the other two)
+// gn_forward_wg.cu: tensor-core edge forward, four warp groups per SM
 int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
                        float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
-int fwd_impl();
 
 // dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
 int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
@@ -431,8 +418,8 @@ int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float
                          cudaStream_t st) {
     const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
     if (math_mode != GCRL_MATH_FP32 && tc_ok)
-        return (fwd_impl() == 2 ? launch_edge_fwd_ws : fwd_impl() == 1 ? launch_edge_fwd_tc : launch_edge_fwd_wg)(
-            b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
+        return launch_edge_fwd_wg(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg,
+                                  var, amin, amax, st);
     return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
 }
 
@@ -544,7 +531,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
     const float* h_prev = x;
     for (int l = 0; l < GCRL_N_BLOCKS; ++l) {
         const bool last = (l == GCRL_N_BLOCKS - 1);
-        const bool keep_e5 = stash_p && math_mode != GCRL_MATH_FP32 && use_ws_kernels();
+        const bool keep_e5 = stash_p && math_mode != GCRL_MATH_FP32;   // block 5 backward then runs as a regular block
         float* e_out = last ? (keep_e5 ? S.e[l] : nullptr) : (stash_p ? S.e[l] : eb[l & 1]);
         float* agg = stash_p ? S.agg[l] : aggb;
         float* hl = stash_p ? S.h[l] : hb[l & 1];

@@ -1,9 +1,9 @@
 // gn_forward_wg.cu -- fused edge kernel of the GN forward pass, four tiles in flight per SM.
 //
-// Same math and fusion as k_edge_fwd_tc (gn_forward_tc.cu; reference: architecture.py:51-66): message MLP on
-// tcgen05 (bf16 / bf16x3 split operands, fp32 accumulate in TMEM), e_l stored by TMA, PNA aggregation fused in.
-// k_edge_fwd_tc runs its phases one after the other in a 256-thread CTA and relies on a second CTA per SM to fill
-// the gaps; its counters say latency: 40 % issue utilisation, a quarter of the stall samples on barriers and
+// Reference: architecture.py:51-66.  Message MLP on tcgen05 (bf16 / bf16x3 split operands, fp32 accumulate in TMEM),
+// e_l stored by TMA, PNA aggregation fused in.  Round 1's first design (removed; git history) ran the
+// phases one after the other in a 256-thread CTA and relied on a second CTA per SM to fill the gaps; its counters
+// said latency: 40 % issue utilisation, a quarter of the stall samples on barriers and
 // another quarter on loads, 16 warps per SM.  Shared memory (110 KB per CTA, 32 KB of it a private copy of the
 // weights) is what stops a third CTA.  This kernel keeps the phase structure but packs FOUR independent 128-thread
 // warp groups into one CTA per SM:
@@ -12,11 +12,10 @@
 //     operand tile (converted in place through registers), the hid operand tile and the fp32 staging tile of m_l
 //     (TMA store source + reducer input);
 //   * Pi[dst] + Pj[src] never touch shared memory: they are gathered in the 16x256b TMEM fragment layout and
-//     written with tcgen05.st, G1 accumulates on top (the backward's trick, gn_backward_ws.cu);
+//     written with tcgen05.st, G1 accumulates on top (as in the backward, gn_backward_wg.cu);
 //   * groups synchronise with named barriers and their own mbarriers only, so one group's MMA / TMA / gather
 //     latency is covered by the other three.
 // TMEM: 128 columns per group (acc1, acc2) = all 512.  Shared memory: 32 + 4 x (32 + 12) + ids = 214 KB.
-#define GCRL_MBAR_TIMEOUT   // counted waits (a protocol bug traps instead of hanging the GPU): measurably faster here than the tight loop (3.27 vs 3.49 ms)
 #include "gn_common.cuh"
 #include "ws.cuh"
 #include <stdlib.h>
@@ -187,7 +186,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             FW_TR(1);
             if (!FIRST) {
                 // ---- e_{l-1}: fp32 landing tile -> bf16 hi/lo operand tile, in place through registers ----------
-                mbar_wait(bar_tma, ph_tma);
+                mbar_wait_bounded(bar_tma, ph_tma);
                 ph_tma ^= 1;
                 FW_TR(2);
                 float4 x[16];
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                     issue_gemm_feat<X3>(t_acc1, smem_u32(Bh), smem_u32(Bl), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
                     umma_commit(bar_mma);
                 }
-                mbar_wait(bar_mma, ph_mma);
+                mbar_wait_bounded(bar_mma, ph_mma);
                 ph_mma ^= 1;
                 tc_fence_after();
             }
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 issue_gemm_feat<X3>(t_acc2, smem_u32(Bh), smem_u32(Bl), smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);
                 umma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, ph_mma);
+            mbar_wait_bounded(bar_mma, ph_mma);
             ph_mma ^= 1;
             tc_fence_after();
             FW_TR(6);
@@ -327,20 +326,7 @@ static int launch_wg_variant(const CUtensorMap& tin, const CUtensorMap& tout, co
     return GCRL_OK;
 }
 
-// GCRL_FWD_IMPL: "wg" (default) this kernel, "tc" the single-group kernel with two CTAs per SM, "ws" the
-// warp-specialised pipeline
-int fwd_impl() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("GCRL_FWD_IMPL");
-        v = 0;
-        if (e && e[0] == 't' && e[1] == 'c') v = 1;
-        if (e && e[0] == 'w' && e[1] == 's') v = 2;
-    }
-    return v;
-}
-
-// Tensor-core edge forward, four warp groups per SM; same contract as launch_edge_fwd_tc (gn_forward_tc.cu).
+// Tensor-core edge forward, four warp groups per SM; same contract as launch_edge_fwd (gn_forward.cu).
 int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
                        float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st) {

@@ -9,7 +9,6 @@
 // TMA store.  The fp32 FFMA kernel k_node_update (gn_forward.cu) stays the parity path of math mode fp32; on the
 // 10 000 x 50-vertex rollout batch it was 29 % of a step (2.05 ms per block, 16 TFLOP/s of FFMA behind 12 LDS per
 // 32 FMA).
-#define GCRL_MBAR_TIMEOUT
 #include "gn_common.cuh"
 #include "tc.cuh"
 
@@ -126,10 +125,10 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
         }
         for (int c = 0; c < nch; ++c) {
             const float* L = (c & 1) ? L1 : L0;
-            mbar_wait(&bar_tma[c & 1], ph_tma[c & 1]);
+            mbar_wait_bounded(&bar_tma[c & 1], ph_tma[c & 1]);
             ph_tma[c & 1] ^= 1u;
             if (c > 0) {                                 // the previous chunk's MMA has read the operand tile
-                mbar_wait(bar_mma, ph_mma);
+                mbar_wait_bounded(bar_mma, ph_mma);
                 ph_mma ^= 1u;
             }
             convert_tile128<X3>(L, reinterpret_cast<__nv_bfloat16*>(Aop), reinterpret_cast<__nv_bfloat16*>(Aop + 16384), tid);
@@ -143,7 +142,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
                 umma_commit(bar_mma);
             }
         }
-        mbar_wait(bar_mma, ph_mma);
+        mbar_wait_bounded(bar_mma, ph_mma);
         ph_mma ^= 1u;
         tc_fence_after();
         // ---- epilogue: bias (+ tail) (+ relu) -> fp32 staging tiles (L0: outputs 0-63, L1: outputs 64-127) ----------------
@@ -315,10 +314,10 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
         if (tid == 0) { issue_load(0, v0); issue_load(1, v0); }
         for (int j = 0; j <= nch; ++j) {
             const float* L = (j & 1) ? L1 : L0;
-            mbar_wait(&bar_tma[j & 1], ph_tma[j & 1]);
+            mbar_wait_bounded(&bar_tma[j & 1], ph_tma[j & 1]);
             ph_tma[j & 1] ^= 1u;
             if (j >= 2) {                                 // the previous chunk's MMA has read Xop
-                mbar_wait(bar_mma, ph_mma);
+                mbar_wait_bounded(bar_mma, ph_mma);
                 ph_mma ^= 1u;
             }
             unsigned char* dstop = j == 0 ? Yop : Xop;
@@ -335,7 +334,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
                 }
             }
         }
-        mbar_wait(bar_mma, ph_mma);                       // all products of this tile are done: Yop / Xop are free
+        mbar_wait_bounded(bar_mma, ph_mma);                       // all products of this tile are done: Yop / Xop are free
         ph_mma ^= 1u;
         first_tile = false;
     }

@@ -73,16 +73,23 @@ static __device__ __noinline__ void mbar_timeout_trap() {
     printf("gcrl: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
     __trap();
 }
-#ifdef GCRL_MBAR_TIMEOUT
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Two wait flavours; each kernel names the one it was measured with.
+//   mbar_wait_bounded: counted try_wait loop -- a protocol bug traps after ~2^22 suspended polls instead of hanging
+//     the GPU.  k_edge_fwd_wg: 3.27 ms per 512-graph launch with it, 3.49 ms with the tight loop (the extra
+//     instructions between polls keep four polling warp groups off each other's issue slots); the vertex-side GEMM
+//     kernels use it too.
+//   mbar_wait_tight: a three-instruction loop.  k_edge_bwd_wg: 5.11 ms vs 5.32 ms with the counted loop (its two
+//     256-thread groups are instruction-fetch bound: every wait site counts).  -DGCRL_MBAR_TIMEOUT turns these into
+//     bounded waits too (debugging build).
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) mbar_timeout_trap();      // try_wait itself sleeps up to its time hint
     }
 }
+#ifdef GCRL_MBAR_TIMEOUT
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_bounded(bar, parity); }
 #else
-// production form: a three-instruction loop (the pipelined kernels are instruction-fetch bound: every wait site
-// counts).  Build with -DGCRL_MBAR_TIMEOUT to turn protocol bugs into traps instead of hangs.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

@@ -1,4 +1,4 @@
-// ws.cuh -- helpers shared by the warp-specialised edge kernels (gn_forward_ws.cu, gn_backward_ws.cu):
+// ws.cuh -- helpers shared by the multi-group edge kernels (gn_forward_wg.cu, gn_backward_wg.cu):
 // mbarrier arrivals per warp, named barriers, TMEM stores in the MMA fragment layout, warp transpose-reduce.
 #pragma once
 #include "tc.cuh"

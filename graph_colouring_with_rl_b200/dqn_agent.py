@@ -90,9 +90,13 @@ class DQNAgentGN():
             self.memory = ReplayBuffer(self.max_buffer_size, len_global_features)
         self.episode_no = 0
         self.last_loss = None          # device scalar of the most recent learn() (not in the reference)
+        self._node_off1, self._node_off1_n = None, -1
 
     # ---- act (dqn_agent.py:108-140) ---------------------------------------------------------------
     def choose_action(self, data, global_features, unassigned_vertices, epsilon=None, test_mode=False):
+        if len(unassigned_vertices) == 0:
+            # the reference raises here too (np.argmax of an empty array / random.choice of an empty list)
+            raise ValueError('choose_action: no unassigned vertex to choose from')
         if epsilon is None:
             if test_mode:
                 epsilon = 0
@@ -106,15 +110,33 @@ class DQNAgentGN():
             gf = torch.tensor(global_features, dtype=torch.float).unsqueeze(0).to(net.device)
             with torch.no_grad():
                 _, action_values = net(gn_input, gf, [0] * n, None)
-            # masked first-argmax on the device (== np.argmax over the ascending unassigned list)
-            mask = np.zeros(n, dtype=np.int32)
-            mask[np.asarray(unassigned_vertices, dtype=np.int64)] = -1
-            colour = torch.from_numpy(mask).to(net.device)
-            node_off = torch.tensor([0, n], dtype=torch.int32, device=net.device)
-            vertex_ind = int(ops.score_argmax(action_values.view(-1), colour, node_off).item())
+            vertex_ind = self._masked_argmax(action_values.view(-1), gn_input, unassigned_vertices, n)
         else:
             vertex_ind = random.choice(unassigned_vertices)
         return vertex_ind
+
+    def _masked_argmax(self, q, data, unassigned_vertices, n):
+        """np.argmax over q[unassigned_vertices] (dqn_agent.py:131-134) as the device's masked first-argmax.
+        np.argmax returns the first maximum IN LIST ORDER; the device kernel returns the lowest vertex index among
+        the maxima, which is the same thing when the list is ascending (it always is in the reference's callers:
+        graph_colouring_env.py:152 rebuilds it in vertex order).  A list that is not ascending takes the literal
+        reference arithmetic on the host.  Fast path: an observation from this package's environment carries the
+        very list object it was built from (`GenerateData_v1` records it), so when the caller passes that list --
+        the reference loop does, dqn_main.py:176 -- the mask is x[:,1] < 0 on the device: no numpy mask, no extra
+        H2D copy; the one unavoidable sync is the `.item()` that returns the Python int."""
+        dev = q.device
+        if self._node_off1 is None or self._node_off1_n != n or self._node_off1.device != dev:
+            self._node_off1 = torch.tensor([0, n], dtype=torch.int32, device=dev)
+            self._node_off1_n = n
+        if getattr(data, '_unassigned', None) is unassigned_vertices and data.x.shape[1] >= 2:
+            colour = data.x[:, 1].to(torch.int32)              # -1 = uncoloured (graph_colouring_env.py:124-128)
+            return int(ops.score_argmax(q, colour, self._node_off1).item())
+        un = np.asarray(unassigned_vertices, dtype=np.int64)
+        if un.size > 1 and np.any(un[1:] <= un[:-1]):
+            return int(un[int(np.argmax(q[torch.from_numpy(un).to(dev)].cpu().numpy()))])
+        mask = np.zeros(n, dtype=np.int32)
+        mask[un] = -1
+        return int(ops.score_argmax(q, torch.from_numpy(mask).to(dev), self._node_off1).item())
 
     def remember(self, data, current_global_features, assigned_vertices, action_ind, reward, next_data,
                  next_global_features, done):
@@ -122,12 +144,21 @@ class DQNAgentGN():
                                      next_data, next_global_features, done)
 
     # ---- learn (dqn_agent.py:147-223) ---------------------------------------------------------------
+    def _dense_ok(self, datas):
+        """The adjacency fast path batches from dense bytes and builds edge_attr = -adj itself, so it is only valid
+        for observations of this package's environment (ColouringData: complete graph, one static -1/0 edge
+        feature).  Anything else -- a caller's own Data with other edge attributes or len_edge_features != 1 --
+        goes through the generic edge-list path."""
+        from .envs import ColouringData
+        return self.gn_behaviour.dims[1] == 1 and all(
+            isinstance(d, ColouringData) and getattr(d, 'adj', None) is not None for d in datas)
+
     def _collate(self, datas, device):
         """-> (packed, eattr internal, x [N,vd], node_off int32 [G+1])."""
         ns = [int(d.x.shape[0]) for d in datas]
         node_off = torch.tensor(np.concatenate([[0], np.cumsum(ns)]), dtype=torch.int32, device=device)
         x = torch.cat([d.x.to(device, torch.float32) for d in datas], 0)
-        if all(getattr(d, 'adj', None) is not None for d in datas):
+        if self._dense_ok(datas):
             adj = torch.cat([d.adj.to(device).reshape(-1) for d in datas])
             nn_ = np.asarray(ns, dtype=np.int64)
             adj_off = torch.tensor(np.concatenate([[0], np.cumsum(nn_ * nn_)[:-1]]), dtype=torch.int64, device=device)
@@ -138,6 +169,22 @@ class DQNAgentGN():
         packed = ops.pack(ei, x.shape[0])
         eattr = ops.permute_rows(b.edge_attr.to(device, torch.float32).reshape(ei.shape[1], -1), packed.perm, True)
         return packed, eattr, x, node_off
+
+    @staticmethod
+    def _same_edges(cur, nxt):
+        """True when every next-state observation shares its edge tensors with the current one (the environment's
+        static per-graph tensors: graph_colouring_env.py:136-137 hands out target['edge_list'] / ['edge_attr'] every
+        step), so one batched layout serves both forwards."""
+        for c, n in zip(cur, nxt):
+            if c.x.shape[0] != n.x.shape[0]:
+                return False
+            for k in ('edge_index', 'edge_attr'):
+                a, b = getattr(c, k), getattr(n, k)
+                if a is b:
+                    continue
+                if a is None or b is None or a.shape != b.shape or a.data_ptr() != b.data_ptr():
+                    return False
+        return True
 
     def learn(self):
         if self.memory.current_mem_size < 10 * self.batch_size:
@@ -157,11 +204,19 @@ class DQNAgentGN():
         cur = [mem.data_memory[i] for i in batch]
         nxt = [mem.next_data_memory[i] for i in batch]
         packed, eattr, x_cur, node_off = self._collate(cur, dev)
-        x_next = torch.cat([d.x.to(dev, torch.float32) for d in nxt], 0)
+        if self._same_edges(cur, nxt):
+            packed_n, eattr_n = packed, eattr
+            x_next = torch.cat([d.x.to(dev, torch.float32) for d in nxt], 0)
+        else:       # the reference batches next_datas separately (dqn_agent.py:55-56,187)
+            packed_n, eattr_n, x_next, _ = self._collate(nxt, dev)
         # assigned-after-step one-hot (dqn_main.py:184) -> "colour >= 0 means assigned"
         assigned = np.concatenate([np.asarray(mem.assigned_vertices_memory[i]).reshape(-1) for i in batch])
         next_colour = torch.from_numpy(np.where(assigned == 1, 0, -1).astype(np.int32)).to(dev)
-        action = torch.from_numpy(mem.action_ind_memory[batch].reshape(-1).astype(np.int32)).to(dev)
+        action_h = mem.action_ind_memory[batch].reshape(-1).astype(np.int64)
+        n_h = np.asarray([int(d.x.shape[0]) for d in cur], dtype=np.int64)
+        if np.any(action_h < 0) or np.any(action_h >= n_h):
+            raise IndexError('replay transition with an action outside its graph: %r' % (action_h[(action_h < 0) | (action_h >= n_h)][:4],))
+        action = torch.from_numpy(action_h.astype(np.int32)).to(dev)
         reward = torch.from_numpy(mem.reward_memory[batch].astype(np.float32)).to(dev)
         done = torch.from_numpy(mem.done_memory[batch].astype(np.int32)).to(dev)
         gfeat = gfeat_n = vgraph = None
@@ -173,7 +228,7 @@ class DQNAgentGN():
         flat_b, flat_t = net_b.flat_params(), net_t.flat_params()
         _, q_cur, stash = ops.gn_forward(flat_b, net_b.dims, packed, x_cur, eattr, gfeat, vgraph, with_stash=True,
                                          math_mode=net_b.math_mode)
-        _, q_next, _ = ops.gn_forward(flat_t, net_t.dims, packed, x_next, eattr, gfeat_n, vgraph,
+        _, q_next, _ = ops.gn_forward(flat_t, net_t.dims, packed_n, x_next, eattr_n, gfeat_n, vgraph,
                                       math_mode=net_t.math_mode)
         loss, q_exp, q_tgt, d_q = ops.td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done,
                                                      self.gamma)

@@ -19,6 +19,17 @@ from .architecture import _device
 from .data import Data
 
 MAX_RADIUS_FOR_NEIGHBOURS = 3      # utils.py:19
+ENV_MAX_N = 4096                   # vertices per graph the env kernels support (csrc/env.cu ENV_MAX_N; colours are int16 in the replay ring)
+
+
+def check_graph_sizes(ns):
+    """The env kernels keep a graph's colours in shared memory: a graph over ENV_MAX_N vertices would be skipped
+    silently (state never advances, `done` never set), so it is rejected here."""
+    ns = np.asarray(ns)
+    if ns.size and int(ns.max()) > ENV_MAX_N:
+        raise ValueError('graph with %d vertices: the device environment supports at most %d' % (int(ns.max()), ENV_MAX_N))
+    if ns.size and int(ns.min()) < 1:
+        raise ValueError('graph without vertices')
 
 
 class ColouringData(Data):
@@ -82,6 +93,7 @@ class _GraphOnDevice(object):
         self.target = target
         adj = adjacency_from_target(target)
         self.n = n = adj.shape[0]
+        check_graph_sizes([n])
         self.adj_np = adj
         self.adj = torch.from_numpy(adj.reshape(-1)).to(device)
         self.adj_off = torch.zeros(1, dtype=torch.int64, device=device)
@@ -168,6 +180,8 @@ class GraphColouring(object):
         x = torch.stack([g.names, torch.from_numpy(np.asarray(col, dtype=np.float32)).to(self.device)], 1)
         data = ColouringData(x=x, edge_index=g.edge_index, edge_attr=g.edge_attr)
         data.adj = g.adj
+        # the list this observation's x[:,1] < 0 mask was derived from (choose_action's device-mask fast path)
+        data._unassigned = current_graph.get('unassigned_vertices') if 'colour' in current_graph else None
         return data, []
 
     def render(self, mode='human', close=False):
@@ -196,6 +210,18 @@ class BatchedColouringEnv(object):
         self._setup(ns, adj, adj_off, dev)
 
     @classmethod
+    def from_flat(cls, ns, flat_adj, device=None):
+        """ns int64 [G] vertex counts, flat_adj uint8 [sum n^2] (ideally pinned host memory): one async H2D copy,
+        no per-graph Python objects."""
+        dev = _device() if device is None else torch.device(device)
+        ns = np.asarray(ns, dtype=np.int64)
+        self = cls.__new__(cls)
+        adj = flat_adj.to(dev, non_blocking=True)
+        adj_off = torch.from_numpy(np.concatenate([[0], np.cumsum(ns * ns)[:-1]]).astype(np.int64)).to(dev)
+        self._setup(ns, adj, adj_off, dev)
+        return self
+
+    @classmethod
     def from_pool(cls, pool, graph_ids):
         """Environment batch over graphs that already live on the device (replay.GraphPool): the
         adjacency bytes are shared with the pool, only the per-graph offsets are built."""
@@ -207,6 +233,7 @@ class BatchedColouringEnv(object):
         return self
 
     def _setup(self, ns, adj, adj_off, dev):
+        check_graph_sizes(ns)
         self.device = dev
         self.n_graphs = int(ns.size)
         self.ns = ns

@@ -138,7 +138,7 @@ def segment_reduce(msg, seg_off, n_vertices, which):
 
 # ---- GN network -----------------------------------------------------------------------------
 def gn_forward(params, dims, packed, x, eattr, gfeat=None, vgraph=None, with_stash=False,
-               math_mode=_lib.GCRL_MATH_FP32, stash=None):
+               math_mode=_lib.GCRL_MATH_FP32, stash=None, ws=None):
     """params: flat fp32 [P]; dims = (vertex_dim, edge_dim, global_dim); x [N,vd]; eattr [E,ed]
     INTERNAL order.  Returns (h [N,64], q [N], stash-or-None)."""
     lib = _lib.load()
@@ -155,7 +155,9 @@ def gn_forward(params, dims, packed, x, eattr, gfeat=None, vgraph=None, with_sta
             stash = torch.empty(nb, dtype=torch.uint8, device=dev)
     else:
         stash = None
-    ws = workspace(lib.gcrl_gn_forward_workspace_bytes(N, E, 1 if with_stash else 0), dev, 'gn')
+    nb_ws = lib.gcrl_gn_forward_workspace_bytes(N, E, 1 if with_stash else 0)
+    if ws is None or ws.numel() < nb_ws:            # ws: a caller-owned workspace (CUDA-graph capture keeps its own)
+        ws = workspace(nb_ws, dev, 'gn')
     with torch.cuda.device(dev):
         check(lib.gcrl_gn_forward(ptr(params), dims[0], dims[1], dims[2], N, E, ptr(packed.seg_off),
                                   ptr(packed.src), ptr(packed.dst), ptr(x), ptr(eattr), ptr(gfeat), ptr(vgraph),
@@ -218,8 +220,11 @@ def score_argmax(q, colour, node_off, want_q=False):
     return (action, qb) if want_q else action
 
 
-def td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done, gamma, batch_total=None):
-    """Returns (loss [1], q_expected [G], q_target [G], d_q [N])."""
+def td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done, gamma, batch_total=None,
+                   loss_out=None, err=None):
+    """Returns (loss [1], q_expected [G], q_target [G], d_q [N]).  loss_out: a [1] tensor the loss is ADDED to
+    (micro-batches accumulate into one scalar); err: int32 [1] set to 1 + g when graph g's action is outside
+    [0, n_g) (that graph then contributes nothing instead of touching memory out of bounds)."""
     lib = _lib.load()
     dev = q_cur.device
     G = int(node_off.numel()) - 1
@@ -228,11 +233,11 @@ def td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done, g
     q_exp = torch.empty(G, dtype=torch.float32, device=dev)
     q_tgt = torch.empty(G, dtype=torch.float32, device=dev)
     d_q = torch.empty_like(q_cur)
-    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(lib.gcrl_td_target_loss(ptr(q_cur.contiguous()), ptr(q_next.contiguous()), ptr(next_colour),
                                       ptr(node_off), G, ptr(action), ptr(reward), ptr(done), float(gamma),
-                                      int(batch_total), ptr(q_exp), ptr(q_tgt), ptr(d_q), ptr(loss),
+                                      int(batch_total), ptr(q_exp), ptr(q_tgt), ptr(d_q), ptr(loss), ptr(err),
                                       stream_ptr(dev)), 'gcrl_td_target_loss')
     return loss, q_exp, q_tgt, d_q
 

@@ -13,7 +13,7 @@ import torch
 
 from . import ops
 from .architecture import _device
-from .envs import adjacency_from_target
+from .envs import adjacency_from_target, check_graph_sizes
 from .trainer import TransitionBatch
 
 
@@ -27,6 +27,7 @@ class GraphPool(object):
                 for g in graphs]
         self.graphs = graphs
         self.ns = np.asarray([m.shape[0] for m in mats], dtype=np.int64)
+        check_graph_sizes(self.ns)
         self.n_max = int(self.ns.max())
         self.adj_off_h = np.concatenate([[0], np.cumsum(self.ns * self.ns)[:-1]]).astype(np.int64)
         self.adj = torch.from_numpy(np.concatenate([m.reshape(-1) for m in mats])).to(dev)

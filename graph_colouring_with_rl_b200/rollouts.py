@@ -5,16 +5,52 @@ neighbour-count rule, then argmax-Q over uncoloured vertices until every graph i
 Per step: gcrl_gn_forward (Q of every vertex of every graph) -> gcrl_score_argmax (masked
 per-graph first-argmax) -> gcrl_env_step (first-fit colour, leaf pass, observation update).
 Finished graphs get action -1 from the argmax (no uncoloured vertex) and are left alone.
+
+Every step of an episode has the same shapes and the same buffers (only the colours change), so the
+step -- about 30 kernel launches -- is captured ONCE into a CUDA graph and replayed: the host issues
+one graph launch per step instead of walking the launch chain through Python and ctypes, which is
+what bounded small shards (1 250 graphs per GPU at N = 8: 3.5 ms per step, a third of it launch gaps).
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 from .envs import BatchedColouringEnv
 
 
+class _GraphedStep(object):
+    """One rollout step captured as a CUDA graph over an environment's fixed buffers."""
+
+    def __init__(self, env, net):
+        self.key = (net.flat_params().data_ptr(), net.math_mode, env.x.data_ptr())
+        packed, eattr = env.packed
+        flat = net.flat_params()
+        dev = env.device
+        lib = _lib.load()
+        # a private workspace: the shared grow-only one may be re-allocated by a later, larger call
+        self.ws = torch.empty(lib.gcrl_gn_forward_workspace_bytes(packed.n_vertices, packed.n_edges, 0), dtype=torch.uint8,
+                              device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode, ws=self.ws)
+            self.action = ops.score_argmax(q, env.colour, env.node_off)
+            env.step(self.action)
+
+    def replay(self):
+        self.graph.replay()
+        return self.action
+
+
+def _eager_step(env, net, packed, eattr, flat):
+    _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
+    a = ops.score_argmax(q, env.colour, env.node_off)
+    env.step(a)
+    return a
+
+
 @torch.no_grad()
-def greedy_rollouts(graphs, net, record=False, sync_every=8, env=None):
+def greedy_rollouts(graphs, net, record=False, sync_every=8, env=None, graph=True):
     """graphs: list of adjacency matrices / target dicts (or pass a ready `env`).
+    graph: replay the step as a CUDA graph (captured after one eager step, cached on the env).
     Returns dict(colours_used int32 [G] (device), steps, env[, actions list of int32 [G]])."""
     if env is None:
         env = BatchedColouringEnv(graphs, device=net.device)
@@ -28,12 +64,22 @@ def greedy_rollouts(graphs, net, record=False, sync_every=8, env=None):
     if record:
         acts.append(a)
     steps, max_steps = 1, int(env.ns.max())
+    graphed = None
+    if graph:
+        graphed = getattr(env, '_graphed_step', None)
+        if graphed is not None and graphed.key != (flat.data_ptr(), net.math_mode, env.x.data_ptr()):
+            graphed = env._graphed_step = None
     while steps < max_steps:
         if steps % sync_every == 0 and bool(env.done.all().item()):
             break
-        _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
-        a = ops.score_argmax(q, env.colour, env.node_off)
-        env.step(a)
+        if graphed is not None:
+            a = graphed.replay()
+            if record:
+                a = a.clone()
+        else:
+            a = _eager_step(env, net, packed, eattr, flat)      # also the warm-up every capture needs
+            if graph and steps + 2 < max_steps:
+                graphed = env._graphed_step = _GraphedStep(env, net)
         if record:
             acts.append(a)
         steps += 1

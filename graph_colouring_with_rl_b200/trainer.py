@@ -4,7 +4,8 @@ bytes, colour vectors before/after the step, action, reward, done -- i.e. what
 dqn_agent.py:147-223 consumes, without per-transition Python objects.  `QLearner` runs the
 learn step over it in micro-batches sized to fit HBM (the edge state of 4096 graphs x 200
 vertices is 41.7 GB per fp32 [E,64] tensor), accumulating one flat gradient, which at
-world_size > 1 is summed with a single NCCL all-reduce (794 KB) before the fused Adam.
+world_size > 1 is summed -- together with the loss and the per-rank graph count, in the tail of the same buffer --
+with a single asynchronous NCCL all-reduce (794 KB) that the fused Adam's stream waits on.
 """
 import numpy as np
 import torch
@@ -78,10 +79,28 @@ class _Slice(object):
         self.packed, self.eattr = ops.pack_dense(self.adj, self.adj_off, self.node_off, self.n_vertices, self.n_edges)
 
 
+def reduce_mean_gradient(gbuf, n_params, group=None, batch_total=None):
+    """The one collective of a multi-GPU learn step.  gbuf = [flat gradient (n_params) | loss | graph count]
+    holds this rank's SUMS.  With `batch_total` given, the sums were already scaled by 1/batch_total (the caller knows
+    the global minibatch size) and the all-reduce finishes the job.  Without it every rank contributed unscaled sums
+    and its own graph count -- ranks may hold different numbers of graphs (shard_range(7, r, 4) gives 1, 2, 2, 2) -- and
+    gradient and loss are divided by the all-reduced count on the device, so the result is the single-process mean
+    over the union minibatch (dqn_agent.py:215: mse_loss over the whole batch) whatever the split.  The collective is
+    issued asynchronously; the consumer's stream waits for it, the host does not."""
+    work = torch.distributed.all_reduce(gbuf, group=group, async_op=True)
+    work.wait()
+    if batch_total is None:
+        gbuf[:n_params + 1].div_(gbuf[n_params + 1])
+    return gbuf
+
+
 class QLearner(object):
-    def __init__(self, agent, max_edges_per_micro_batch=512 * 200 * 199, process_group=None, local_only=False):
+    def __init__(self, agent, max_edges_per_micro_batch=512 * 200 * 199, process_group=None, local_only=False,
+                 sync_params=True):
         """local_only: never communicate, even inside an initialised process group (a learner that only some ranks
-        run, e.g. the single-GPU training loop, must not enter collectives the other ranks do not)."""
+        run, e.g. the single-GPU training loop, must not enter collectives the other ranks do not).
+        sync_params: at world_size > 1 broadcast rank 0's behaviour and target parameters (and Adam state) once, so
+        that the replicas are identical whatever each rank's seed was."""
         self.agent = agent
         self.max_edges = int(max_edges_per_micro_batch)
         self.group = process_group
@@ -90,6 +109,34 @@ class QLearner(object):
                                (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self._stash = None
+        self._gbuf = None
+        self.keep_q = False              # tests: keep (q_expected, q_target) of the last fwd_bwd
+        self.last_q = None
+        if self.world > 1 and sync_params and hasattr(agent, 'gn_behaviour'):
+            self.broadcast_params()
+
+    def broadcast_params(self, src=0):
+        agent = self.agent
+        nets = [agent.gn_behaviour] + ([agent.gn_target] if hasattr(agent, 'gn_target') else [])
+        for net in nets:
+            torch.distributed.broadcast(net.flat_params(), src=src, group=self.group)
+        opt = agent.gn_behaviour.optimizer
+        if opt.exp_avg is not None:
+            torch.distributed.broadcast(opt.exp_avg, src=src, group=self.group)
+            torch.distributed.broadcast(opt.exp_avg_sq, src=src, group=self.group)
+
+    def _grad_buffer(self):
+        """[P + 2] floats: the behaviour net's flat gradient, then the loss and this rank's graph count -- one buffer,
+        one all-reduce.  The net's `_flat_grad` (what FusedAdam reads) is the leading view."""
+        net = self.agent.gn_behaviour
+        flat = net.flat_params()
+        P = flat.numel()
+        g = self._gbuf
+        if g is None or g.device != flat.device or g.numel() != P + 2 or net._flat_grad is None \
+                or net._flat_grad.data_ptr() != g.data_ptr():
+            g = self._gbuf = torch.zeros(P + 2, dtype=torch.float32, device=flat.device)
+            net._flat_grad = g[:P]
+        return g, P
 
     @torch.no_grad()
     def target_q(self, batch):
@@ -105,46 +152,56 @@ class QLearner(object):
         return out
 
     @torch.no_grad()
-    def fwd_bwd(self, batch, q_next):
-        """Behaviour forward, TD loss against q_next, backward.  Leaves the (all-reduced) mean
-        gradient in the behaviour net's flat gradient buffer and returns the loss [1]."""
+    def fwd_bwd(self, batch, q_next, batch_total=None):
+        """Behaviour forward, TD loss against q_next, backward.  Leaves the mean gradient over the GLOBAL minibatch
+        (all ranks' graphs) in the behaviour net's flat gradient buffer and returns the global loss [1] (a view of the
+        reduction buffer: read or clone it before the next call).  batch_total: the global number of graphs if the
+        caller knows it; otherwise it is all-reduced together with the gradient (see reduce_mean_gradient)."""
         agent = self.agent
         net = agent.gn_behaviour
         flat = net.flat_params()
-        if net._flat_grad is None:
-            net._flat_grad = torch.zeros_like(flat)
-        grad = net._flat_grad
-        total = batch.n_graphs * self.world
-        loss = torch.zeros(1, dtype=torch.float32, device=batch.device)
+        gbuf, P = self._grad_buffer()
+        grad, loss = gbuf[:P], gbuf[P:P + 1]
+        gbuf[P:].zero_()
+        if self.world == 1:
+            total = batch.n_graphs if batch_total is None else int(batch_total)
+        else:
+            total = 1 if batch_total is None else int(batch_total)     # unscaled sums, normalised after the reduce
+            gbuf[P + 1] = float(batch.n_graphs)
         first = True
+        kept = []
         for g0, g1 in batch.micro_ranges(self.max_edges):
             s = _Slice(batch, g0, g1)
             x = batch.x_of(batch.cur_colour[s.v0:s.v1], s.v0, s.v1)
             _, q, self._stash = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, with_stash=True,
                                                math_mode=net.math_mode, stash=self._stash)
-            l, _, _, d_q = ops.td_target_loss(q, q_next[s.v0:s.v1], batch.next_colour[s.v0:s.v1], s.node_off,
-                                              batch.action[g0:g1], batch.reward[g0:g1], batch.done[g0:g1],
-                                              agent.gamma, batch_total=total)
-            loss += l
+            _, q_exp, q_tgt, d_q = ops.td_target_loss(q, q_next[s.v0:s.v1], batch.next_colour[s.v0:s.v1], s.node_off,
+                                                      batch.action[g0:g1], batch.reward[g0:g1], batch.done[g0:g1],
+                                                      agent.gamma, batch_total=total, loss_out=loss)
+            if self.keep_q:
+                kept.append((q_exp, q_tgt))
             ops.gn_backward(flat, net.dims, s.packed, x, s.eattr, self._stash, d_q=d_q, grad=grad,
                             accumulate=not first, math_mode=net.math_mode)
             first = False
+        if first:
+            grad.zero_()                                                # a rank without graphs still joins the reduce
+        if self.keep_q:
+            self.last_q = (torch.cat([k[0] for k in kept]), torch.cat([k[1] for k in kept])) if kept else None
         if self.world > 1:
-            torch.distributed.all_reduce(grad, group=self.group)        # sum of per-rank (1/B_global)-scaled grads
-            torch.distributed.all_reduce(loss, group=self.group)
+            reduce_mean_gradient(gbuf, P, self.group, batch_total)
         return loss
 
     @torch.no_grad()
-    def learn_step(self, batch):
+    def learn_step(self, batch, batch_total=None):
         """dqn_agent.py:147-223 on a TransitionBatch: target forward, behaviour forward/backward,
         fused Adam + soft target update."""
         agent = self.agent
         q_next = self.target_q(batch)
-        loss = self.fwd_bwd(batch, q_next)
+        loss = self.fwd_bwd(batch, q_next, batch_total)
         agent.gn_behaviour.optimizer.step(target_flat=agent.gn_target.flat_params(), tau=agent.tau,
                                           grad=agent.gn_behaviour._flat_grad)
-        agent.last_loss = loss
-        return loss
+        agent.last_loss = loss.clone()
+        return agent.last_loss
 
 
 @torch.no_grad()
@@ -175,6 +232,22 @@ def synthetic_transitions(adjs, frac_coloured, seed, device):
     host = dict(adj=env.adj.cpu(), cur_colour=cur.cpu(), next_colour=env.colour.cpu(), action=act.cpu(),
                 reward=env.reward.cpu(), done=env.done.cpu())
     return env.ns.copy(), host
+
+
+def shard_host(ns, host, lo, hi):
+    """Graphs [lo, hi) of a host transition dict (FIELDS) -> (ns[lo:hi], dict of views; pinned stays pinned)."""
+    ns = np.asarray(ns, dtype=np.int64)
+    node_off = np.concatenate([[0], np.cumsum(ns)])
+    adj_off = np.concatenate([[0], np.cumsum(ns * ns)])
+    v0, v1, a0, a1 = int(node_off[lo]), int(node_off[hi]), int(adj_off[lo]), int(adj_off[hi])
+    return ns[lo:hi], dict(adj=host['adj'][a0:a1], cur_colour=host['cur_colour'][v0:v1],
+                           next_colour=host['next_colour'][v0:v1], action=host['action'][lo:hi],
+                           reward=host['reward'][lo:hi], done=host['done'][lo:hi])
+
+
+def shard_batch(ns, host, lo, hi, device):
+    """This rank's contiguous slice of a global minibatch as a device TransitionBatch (split by graph)."""
+    return TransitionBatch.from_host(*shard_host(ns, host, lo, hi), device)
 
 
 def shard_range(n_items, rank, world):

@@ -175,12 +175,14 @@ int gcrl_score_argmax(const float* q, const int32_t* colour, const int32_t* node
  * vertex layout), next_colour [N] (>= 0 = assigned after the step), action[G] local vertex
  * index, reward[G], done[G].  Writes q_expected[G], q_target[G], d_q[N] (2/B_total *
  * (q_exp - q_tgt) at the action vertex, 0 elsewhere) and adds sum_g (q_exp-q_tgt)^2 / B_total
- * into loss[0] (caller zeroes it).  B_total = global minibatch size (all ranks). */
+ * into loss[0] (caller zeroes it).  B_total = global minibatch size (all ranks).  A graph whose
+ * action is outside [0, n_g) contributes nothing (q_expected / q_target = NaN for it) and sets
+ * *err = g + 1 (err may be NULL; caller zeroes it): no out-of-bounds access on a sentinel action. */
 int gcrl_td_target_loss(const float* q_cur, const float* q_next, const int32_t* next_colour,
                         const int32_t* node_off, int32_t n_graphs, const int32_t* action,
                         const float* reward, const int32_t* done, float gamma,
                         int32_t batch_total, float* q_expected, float* q_target, float* d_q,
-                        float* loss, void* stream);
+                        float* loss, int32_t* err, void* stream);
 
 /* ---- fused Adam + soft target update (architecture.py:173 torch.optim.Adam defaults;
  * dqn_agent.py:220,223,226-229) ------------------------------------------------------------

@@ -1,8 +1,6 @@
-"""The alternative edge-kernel implementations are selected by environment variables that the library reads once
-per process, so they are exercised in a child pytest run: the default dispatch is the multi-group pair
-(k_edge_fwd_wg / k_edge_bwd_wg); the single-group and warp-specialised forward (GCRL_FWD_IMPL=tc / ws), the
-warp-specialised and single-group backward (GCRL_EDGE_IMPL=ws / tc) and the fp32 vertex side under the tensor-core
-edge kernels (GCRL_NODE_IMPL=ffma) must pass the same tensor-core parity tests."""
+"""The fp32 vertex side under the tensor-core edge kernels (GCRL_NODE_IMPL=ffma) is selected by an environment variable
+the library reads once per process, so it is exercised in a child pytest run and must pass the same tensor-core parity
+tests.  (Round 1's superseded edge kernels -- single-group and warp-specialised -- were removed in round 2.)"""
 import os
 import subprocess
 import sys
@@ -13,8 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize('env', [{'GCRL_FWD_IMPL': 'ws'}, {'GCRL_FWD_IMPL': 'tc'}, {'GCRL_EDGE_IMPL': 'ws'},
-                                 {'GCRL_EDGE_IMPL': 'tc'}, {'GCRL_NODE_IMPL': 'ffma'}])
+@pytest.mark.parametrize('env', [{'GCRL_NODE_IMPL': 'ffma'}])
 def test_alternative_implementation_passes_tensor_core_parity(env):
     if os.environ.get('GCRL_ALT_CHILD'):
         pytest.skip('child run')

@@ -1,8 +1,10 @@
-"""World-size-2 gloo test (CPU) of the N>1 learning rule: each rank scales its
-minibatch shard's loss by 1/B_global, the flat gradients are summed with one all-reduce, and the
-result equals the single-process gradient on the whole minibatch.  The arithmetic here is the
-oracle's (the CUDA path cannot run on CPU); what is under test is the sharding/all-reduce contract
-QLearner implements, plus the host-side shard and micro-batch helpers."""
+"""World-size-2 gloo test (CPU) of the N>1 learning rule through the function QLearner itself calls
+(`trainer.reduce_mean_gradient`): every rank puts the SUMS of its shard -- flat gradient, loss, graph count -- into
+one buffer, one all-reduce, and the result equals the single-process mean gradient on the whole minibatch, for an
+UNEQUAL split (7 graphs over 2 ranks: 3 + 4; a per-rank 1/(n_local * world) scaling would be wrong here) and through
+both normalisation routes (global size known to the caller / all-reduced with the gradient).  The per-shard
+arithmetic here is the oracle's (the CUDA path cannot run on CPU; tests/test_multigpu_gpu.py runs the same check on
+two real GPUs); also covered: the host-side shard and micro-batch helpers."""
 import os
 
 import numpy as np
@@ -29,10 +31,10 @@ def _loss_grads(params, obs, actions, targets, b_total):
 def _make_batch():
     graphs = util.load_validation_graphs()
     rng = np.random.default_rng(0)
-    gids = [1, 5, 9, 30, 47, 66]
+    gids = [1, 5, 9, 30, 47, 66, 12]
     obs = [gn_oracle.observation(graphs[g]['adj'], util.random_colours(graphs[g]['n'], graphs[g]['adj'], 0.4, rng),
                                  graphs[g]['edge_list']) for g in gids]
-    actions = np.asarray([0, 3, 2, 7, 1, 4])
+    actions = np.asarray([0, 3, 2, 7, 1, 4, 5])
     targets = rng.standard_normal(len(gids)).astype(np.float32)
     return obs, actions, targets
 
@@ -47,15 +49,21 @@ def _worker(rank, world, port, out_dir):
     # pick up the default process group: it would enter all-reduces the other ranks never post
     from graph_colouring_with_rl_b200.trainer import QLearner
     assert QLearner(object()).world == world and QLearner(object(), local_only=True).world == 1
+    from graph_colouring_with_rl_b200.trainer import reduce_mean_gradient
     params = util.load_parity_weights()
     obs, actions, targets = _make_batch()
     lo, hi = shard_range(len(obs), rank, world)
-    loss, grad = _loss_grads(params, obs[lo:hi], actions[lo:hi], targets[lo:hi], len(obs))
-    loss_t = torch.tensor([loss])
-    dist.all_reduce(grad)
-    dist.all_reduce(loss_t)
+    assert (hi - lo) == (3 if rank == 0 else 4)
+    out = {}
+    for tag, total in (('count_allreduced', None), ('batch_total_given', len(obs))):
+        # unscaled sums (b_total = 1) when the count rides in the buffer, else scaled by the known global size
+        loss, grad = _loss_grads(params, obs[lo:hi], actions[lo:hi], targets[lo:hi], 1 if total is None else total)
+        P = grad.numel()
+        gbuf = torch.cat([grad, torch.tensor([loss, float(hi - lo)])])
+        reduce_mean_gradient(gbuf, P, None, total)
+        out[tag] = {'grad': gbuf[:P].clone(), 'loss': float(gbuf[P])}
     if rank == 0:
-        torch.save({'grad': grad, 'loss': float(loss_t)}, os.path.join(out_dir, 'reduced.pt'))
+        torch.save(out, os.path.join(out_dir, 'reduced.pt'))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,9 +75,14 @@ def test_two_rank_gradient_allreduce_equals_single_process(tmp_path):
     params = util.load_parity_weights()
     obs, actions, targets = _make_batch()
     loss, grad = _loss_grads(params, obs, actions, targets, len(obs))
-    assert abs(got['loss'] - loss) < 1e-5 * max(1.0, abs(loss))
     scale = float(grad.abs().max())
-    assert float((got['grad'] - grad).abs().max()) < 5e-3 * scale
+    for tag in ('count_allreduced', 'batch_total_given'):
+        assert abs(got[tag]['loss'] - loss) < 1e-5 * max(1.0, abs(loss)), tag
+        assert float((got[tag]['grad'] - grad).abs().max()) < 5e-3 * scale, tag
+    # what the round-1 rule (each rank scales by 1 / (n_local * world)) would have produced on this split: wrong
+    l0, g0 = _loss_grads(params, obs[:3], actions[:3], targets[:3], 3 * 2)
+    l1, g1 = _loss_grads(params, obs[3:], actions[3:], targets[3:], 4 * 2)
+    assert float((g0 + g1 - grad).abs().max()) > 2e-2 * scale
 
 
 def test_shard_and_micro_batch_helpers():
@@ -80,3 +93,10 @@ def test_shard_and_micro_batch_helpers():
         assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
         sizes = [b - a for a, b in parts]
         assert max(sizes) - min(sizes) <= 1
+    from graph_colouring_with_rl_b200.trainer import shard_host
+    ns = np.asarray([3, 5, 2, 4])
+    host = dict(adj=torch.arange(int((ns * ns).sum())), cur_colour=torch.arange(14), next_colour=torch.arange(14) + 100,
+                action=torch.arange(4), reward=torch.arange(4.), done=torch.arange(4))
+    n2, h2 = shard_host(ns, host, 1, 3)
+    assert list(n2) == [5, 2] and h2['adj'].tolist() == list(range(9, 9 + 29)) and h2['cur_colour'].tolist() == list(range(3, 10))
+    assert h2['next_colour'].tolist() == list(range(103, 110)) and h2['action'].tolist() == [1, 2]
