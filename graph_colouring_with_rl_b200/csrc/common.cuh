@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/gcrl_b200.h"
 
 #define HID GCRL_HID
@@ -16,6 +17,16 @@ int sm_count();
 void count_launch(int n);                       // prof.cu: kernels launched by the library
 int prof_begin(int kind, cudaStream_t st);      // prof.cu: event timing when enabled, else -1
 void prof_end(int token, cudaStream_t st);
+
+// NVTX range for the profilers' timelines (nsys / ncu --nvtx): header-only nvtx3, a no-op pointer check unless a tool
+// is attached.  One range per entry point and per block / direction inside the network passes.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    NvtxRange(const char* fmt, int a) { char b[64]; snprintf(b, sizeof b, fmt, a); nvtxRangePushA(b); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 #define GCRL_CHECK_ARG(cond)                                                          \
     do {                                                                              \

@@ -563,6 +563,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         set_error("gcrl_gn_backward: workspace too small");
         return GCRL_ERR_WORKSPACE;
     }
+    NvtxRange nv_all("gcrl_gn_backward");
     Stash S = carve_stash(const_cast<void*>(stash_p), N, E);
     Arena ar(ws, ws_bytes);
     float* deb[2] = {ar.take<float>((size_t)E * 64), ar.take<float>((size_t)E * 64)};
@@ -582,6 +583,8 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
     const HeadW& hd = net.head;
     const int ldF1 = 64 + hd.Dg;
     const float* h5 = S.h[GCRL_N_BLOCKS - 1];
+    {
+    NvtxRange nv_h("bwd head");
     if (d_q) {
         float* dy2 = du1;       // reuse
         float* dy1 = scratch;
@@ -614,9 +617,11 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         GCRL_CUDA(cudaMemcpyAsync(dh, d_h, (size_t)N * 64 * 4, cudaMemcpyDeviceToDevice, st));
     }
 
+    }
     // ---- blocks 5..1 ------------------------------------------------------------------------------
     const float* de_cur = nullptr;   // d e_l
     for (int l = GCRL_N_BLOCKS - 1; l >= 0; --l) {
+        NvtxRange nv_blk("bwd block %d", l + 1);
         const BlockW& b = net.blk[l];
         const float* h_prev = (l == 0) ? x : S.h[l - 1];
         const int ldU1 = 256 + b.Dv;

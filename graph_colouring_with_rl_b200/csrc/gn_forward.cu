@@ -502,6 +502,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
     }
     rc = set_smem_attrs();
     if (rc) return rc;
+    NvtxRange nv_all("gcrl_gn_forward");
     cudaStream_t st = (cudaStream_t)stream;
     NetW net = make_net(params, vdim, edim, gdim);
     Arena ar(ws, ws_bytes);
@@ -535,10 +536,15 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         float* e_out = last ? (keep_e5 ? S.e[l] : nullptr) : (stash_p ? S.e[l] : eb[l & 1]);
         float* agg = stash_p ? S.agg[l] : aggb;
         float* hl = stash_p ? S.h[l] : hb[l & 1];
+        NvtxRange nv_blk("fwd block %d", l + 1);
+        {
+        NvtxRange nv_e("edge: message MLP + PNA");
         rc = launch_edge_fwd_mode(math_mode, net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
                              seg_off, src, dst, N, E, e_out, agg, stash_p ? S.var[l] : nullptr,
                              stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st);
+        }
         if (rc) return rc;
+        NvtxRange nv_v(last ? "vertex: update MLP + head" : "vertex: update MLP + next projections");
         float* Pin = (stash_p && !last) ? S.Pi[l + 1] : Pi;
         float* Pjn = (stash_p && !last) ? S.Pj[l + 1] : Pj;
         const int Dv_l = net.blk[l].Dv;
