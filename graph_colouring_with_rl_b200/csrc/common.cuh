@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <math.h>
+#include <stdlib.h>
 #include <nvtx3/nvToolsExt.h>
 #include "../../include/gcrl_b200.h"
 
@@ -17,6 +18,35 @@ int sm_count();
 void count_launch(int n);                       // prof.cu: kernels launched by the library
 int prof_begin(int kind, cudaStream_t st);      // prof.cu: event timing when enabled, else -1
 void prof_end(int token, cudaStream_t st);
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// The small-batch paths (a 64-transition learn step, batch-1 act, rollouts of a few hundred graphs) are chains of
+// ~10 us kernels, each depending on the one before: the launch gap is a third of their time.  Every kernel of the
+// library starts with pdl_prologue(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be launched
+// (its CTAs scheduled, parameters fetched) while this one still runs; `griddepcontrol.wait` then blocks until the
+// PREVIOUS kernel has completed and its memory is visible -- before this kernel touches any global memory, so the
+// stream's data dependences hold exactly as without PDL (transitively: no kernel completes before its own wait).
+// launch_k() launches with the programmatic-stream-serialization attribute (GCRL_PDL=0 switches it off: the two PTX
+// instructions are then no-ops).  Works under CUDA-graph capture (programmatic edges).
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();   // prof.cu
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // NVTX range for the profilers' timelines (nsys / ncu --nvtx): header-only nvtx3, a no-op pointer check unless a tool
 // is attached.  One range per entry point and per block / direction inside the network passes.

@@ -29,6 +29,7 @@ __device__ __forceinline__ void warp_masked_argmax(const float* __restrict__ q,
 __global__ void k_score_argmax(const float* __restrict__ q, const int32_t* __restrict__ colour,
                                const int32_t* __restrict__ node_off, int32_t G,
                                int32_t* __restrict__ action, float* __restrict__ q_best) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -51,6 +52,7 @@ __global__ void k_td_target_loss(const float* __restrict__ q_cur, const float* _
                                  const int32_t* __restrict__ done, float gamma, float inv_b,
                                  float* __restrict__ q_expected, float* __restrict__ q_target,
                                  float* __restrict__ d_q, float* __restrict__ loss, int32_t* __restrict__ err) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -91,6 +93,7 @@ __global__ void k_adam_soft_update(float* __restrict__ p, const float* __restric
                                    float* __restrict__ t, int64_t n, float one_minus_b1, float b2,
                                    float one_minus_b2, float step_size, float bc2_sqrt, float eps,
                                    float tau, float one_minus_tau) {
+    pdl_prologue();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const float gi = g[i];
@@ -108,6 +111,7 @@ __global__ void k_adam_soft_update(float* __restrict__ p, const float* __restric
 
 __global__ void k_soft_update(const float* __restrict__ b, float* __restrict__ t, int64_t n, float tau,
                               float one_minus_tau) {
+    pdl_prologue();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
         t[i] = __fadd_rn(__fmul_rn(tau, b[i]), __fmul_rn(one_minus_tau, t[i]));
@@ -138,7 +142,7 @@ int gcrl_score_argmax(const float* q, const int32_t* colour, const int32_t* node
     GCRL_CHECK_ARG(G >= 0);
     if (G == 0) return GCRL_OK;
     GCRL_CHECK_ARG(q && colour && node_off && action);
-    k_score_argmax<<<warp_grid(G), 256, 0, (cudaStream_t)stream>>>(q, colour, node_off, G, action, q_best);
+    launch_k(k_score_argmax, dim3(warp_grid(G)), dim3(256), 0, (cudaStream_t)stream, q, colour, node_off, G, action, q_best);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -150,8 +154,7 @@ int gcrl_td_target_loss(const float* q_cur, const float* q_next, const int32_t* 
     GCRL_CHECK_ARG(G >= 0 && batch_total >= 1);
     if (G == 0) return GCRL_OK;
     GCRL_CHECK_ARG(q_cur && q_next && next_colour && node_off && action && reward && done && d_q && loss);
-    k_td_target_loss<<<warp_grid(G), 256, 0, (cudaStream_t)stream>>>(
-        q_cur, q_next, next_colour, node_off, G, action, reward, done, gamma, 1.0f / (float)batch_total,
+    launch_k(k_td_target_loss, dim3(warp_grid(G)), dim3(256), 0, (cudaStream_t)stream, q_cur, q_next, next_colour, node_off, G, action, reward, done, gamma, 1.0f / (float)batch_total,
         q_expected, q_target, d_q, loss, err);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -168,8 +171,7 @@ int gcrl_adam_soft_update(float* params, const float* grad, float* exp_avg, floa
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
-    k_adam_soft_update<<<elem_grid(n), 256, 0, (cudaStream_t)stream>>>(
-        params, grad, exp_avg, exp_avg_sq, target, n, (float)(1.0 - (double)beta1), beta2,
+    launch_k(k_adam_soft_update, dim3(elem_grid(n)), dim3(256), 0, (cudaStream_t)stream, params, grad, exp_avg, exp_avg_sq, target, n, (float)(1.0 - (double)beta1), beta2,
         (float)(1.0 - (double)beta2), step_size, bc2_sqrt, eps, tau, (float)(1.0 - (double)tau));
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -179,7 +181,7 @@ int gcrl_soft_update(const float* behaviour, float* target, int64_t n, float tau
     GCRL_CHECK_ARG(n >= 0);
     if (n == 0) return GCRL_OK;
     GCRL_CHECK_ARG(behaviour && target);
-    k_soft_update<<<elem_grid(n), 256, 0, (cudaStream_t)stream>>>(behaviour, target, n, tau,
+    launch_k(k_soft_update, dim3(elem_grid(n)), dim3(256), 0, (cudaStream_t)stream, behaviour, target, n, tau,
                                                                  (float)(1.0 - (double)tau));
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;

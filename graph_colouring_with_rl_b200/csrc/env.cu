@@ -20,6 +20,7 @@ constexpr int ENV_WORDS = ENV_MAX_N / 32;
 __global__ void k_env_reset(int32_t* __restrict__ colour, int32_t* __restrict__ max_colour,
                             float* __restrict__ x, const int32_t* __restrict__ node_off, int32_t G,
                             int64_t N) {
+    pdl_prologue();
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t v = t; v < N; v += stride) colour[v] = -1;
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(ENV_THREADS) k_env_step(
     const int32_t* __restrict__ node_off, int32_t G, const int32_t* __restrict__ action,
     int32_t* __restrict__ colour, int32_t* __restrict__ max_colour, float* __restrict__ reward,
     int32_t* __restrict__ done, float* __restrict__ x, int32_t* __restrict__ err) {
+    pdl_prologue();
     __shared__ int32_t col_s[ENV_MAX_N];
     __shared__ uint32_t used_s[ENV_WARPS][ENV_WORDS];
     __shared__ int32_t maxc_s, uncol_s;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(ENV_THREADS) k_env_first_vertex(
     const uint8_t* __restrict__ adj, const int64_t* __restrict__ adj_off,
     const int32_t* __restrict__ node_off, int32_t G, int32_t* __restrict__ action,
     int32_t* __restrict__ dist_counts, int32_t* __restrict__ err) {
+    pdl_prologue();
     __shared__ uint8_t dist_s[ENV_WARPS][ENV_MAX_N];
     __shared__ long long best_score[ENV_WARPS];
     __shared__ int32_t best_v[ENV_WARPS];
@@ -207,7 +210,7 @@ int gcrl_env_reset(int32_t* colour, int32_t* max_colour, float* x, const int32_t
     int64_t work = N > G ? N : G;
     int blocks = (int)((work + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    k_env_reset<<<blocks, 256, 0, (cudaStream_t)stream>>>(colour, max_colour, x, node_off, G, N);
+    launch_k(k_env_reset, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, colour, max_colour, x, node_off, G, N);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -219,7 +222,7 @@ int gcrl_env_step(const uint8_t* adj, const int64_t* adj_off, const int32_t* nod
     if (G == 0) return GCRL_OK;
     GCRL_CHECK_ARG(adj && adj_off && node_off && action && colour && max_colour);
     int blocks = G < sm_count() * 16 ? G : sm_count() * 16;
-    k_env_step<<<blocks, ENV_THREADS, 0, (cudaStream_t)stream>>>(adj, adj_off, node_off, G, action, colour,
+    launch_k(k_env_step, dim3(blocks), dim3(ENV_THREADS), 0, (cudaStream_t)stream, adj, adj_off, node_off, G, action, colour,
                                                                 max_colour, reward, done, x, nullptr);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -231,7 +234,7 @@ int gcrl_env_first_vertex(const uint8_t* adj, const int64_t* adj_off, const int3
     if (G == 0) return GCRL_OK;
     GCRL_CHECK_ARG(adj && adj_off && node_off && (action || dist_counts));
     int blocks = G < sm_count() * 16 ? G : sm_count() * 16;
-    k_env_first_vertex<<<blocks, ENV_THREADS, 0, (cudaStream_t)stream>>>(adj, adj_off, node_off, G, action,
+    launch_k(k_env_first_vertex, dim3(blocks), dim3(ENV_THREADS), 0, (cudaStream_t)stream, adj, adj_off, node_off, G, action,
                                                                         dist_counts, nullptr);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;

@@ -36,6 +36,7 @@ constexpr int GB = 64;   // tile M = N
 constexpr int GK = 16;   // tile K
 
 __global__ void __launch_bounds__(256) k_sgemm(const GemmArgs g) {
+    pdl_prologue();
     __shared__ __align__(16) float As[GK][GB + 4];
     __shared__ __align__(16) float Bs[GK][GB + 4];
     const int tid = threadIdx.x;
@@ -114,7 +115,7 @@ static int launch_gemm(GemmArgs g, cudaStream_t st) {
     }
     int64_t gz = g.K > 0 ? (g.K + g.k_chunk - 1) / g.k_chunk : 1;
     dim3 grid((unsigned)((g.M + GB - 1) / GB), (unsigned)((g.N + GB - 1) / GB), (unsigned)gz);
-    k_sgemm<<<grid, 256, 0, st>>>(g);
+    launch_k(k_sgemm, dim3(grid), dim3(256), 0, st, g);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -146,6 +147,7 @@ static int dgrad(const float* dY, int ldy, int O, const float* W, int ldw, int w
 // out[c] += sum_r Y[r][c], width <= 64
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ Y, int64_t R, int width,
                                                float* __restrict__ out) {
+    pdl_prologue();
     __shared__ float part[4][64];
     const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
     float s = 0.f;
@@ -161,13 +163,14 @@ static int colsum(const float* Y, int64_t R, int width, float* out, cudaStream_t
     int64_t blocks = (R + 3) / 4;
     int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
-    k_colsum<<<(int)blocks, 256, 0, st>>>(Y, R, width, out);
+    launch_k(k_colsum, dim3((int)blocks), dim3(256), 0, st, Y, R, width, out);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
 
 __global__ void k_gather_rows(const float* __restrict__ table, const int32_t* __restrict__ idx,
                               int64_t R, int width, float* __restrict__ out) {
+    pdl_prologue();
     int64_t total = R * width;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -178,6 +181,7 @@ __global__ void k_gather_rows(const float* __restrict__ table, const int32_t* __
 }
 
 __global__ void k_add_inplace(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+    pdl_prologue();
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n;
          t += (int64_t)gridDim.x * blockDim.x)
         a[t] += b[t];
@@ -233,6 +237,7 @@ __device__ __forceinline__ void wgrad_tile(const float (*Y)[LDT], const float (*
 
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 1) k_edge_bwd(const EdgeBwdArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EdgeBwdSmem& S = *reinterpret_cast<EdgeBwdSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -505,8 +510,8 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
     int64_t grid = sm_count();
     if (grid > tiles) grid = tiles;
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (a.m ? GCRL_PROF_EDGE_BWD : GCRL_PROF_EDGE_BWD_LAST), st);
-    if (first) k_edge_bwd<true><<<(int)grid, 256, sizeof(EdgeBwdSmem), st>>>(a);
-    else k_edge_bwd<false><<<(int)grid, 256, sizeof(EdgeBwdSmem), st>>>(a);
+    if (first) launch_k(k_edge_bwd<true>, dim3((int)grid), dim3(256), sizeof(EdgeBwdSmem), st, a);
+    else launch_k(k_edge_bwd<false>, dim3((int)grid), dim3(256), sizeof(EdgeBwdSmem), st, a);
     prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -600,7 +605,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             int64_t total = N * hd.Dg;
             int blocks = (int)((total + 255) / 256);
             if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-            k_gather_rows<<<blocks, 256, 0, st>>>(gfeat, vgraph, N, hd.Dg, dh_prev);
+            launch_k(k_gather_rows, dim3(blocks), dim3(256), 0, st, gfeat, vgraph, N, hd.Dg, dh_prev);
             GCRL_LAUNCH_CHECK();
             RC(wgrad(dy1, 64, 64, dh_prev, hd.Dg, hd.Dg, G(hd.F1), ldF1, 64, N, st));
         }
@@ -610,7 +615,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             int64_t n = N * 64;
             int blocks = (int)((n + 255) / 256);
             if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-            k_add_inplace<<<blocks, 256, 0, st>>>(dh, d_h, n);
+            launch_k(k_add_inplace, dim3(blocks), dim3(256), 0, st, dh, d_h, n);
             GCRL_LAUNCH_CHECK();
         }
     } else {

@@ -54,6 +54,7 @@ __global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __re
                                float* __restrict__ ca, float* __restrict__ cb, const int32_t* __restrict__ amin,
                                const int32_t* __restrict__ amax, float* __restrict__ de_scatter,
                                float* __restrict__ gb2_vertex) {
+    pdl_prologue();
     // gb2_vertex != null (block 5, pipelined kernel): db2 = sum over edges of dm = sum_v (g_mean + g_min + g_max)
     // (the std term sums to zero over a segment), accumulated here instead of in the edge kernel
     float bacc = 0.f;
@@ -94,7 +95,7 @@ int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, c
     int64_t blocks = (N * 64 + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k_pna_bwd_coef<<<(int)blocks, 256, 0, st>>>(dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex);
+    launch_k(k_pna_bwd_coef, dim3((int)blocks), dim3(256), 0, st, dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                                                                const __grid_constant__ CUtensorMap tm_dpj,
                                                                const __grid_constant__ CUtensorMap tm_dpj8,
                                                                const BwdWgArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     BwdWgSmem& S = *reinterpret_cast<BwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, grp = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
@@ -589,7 +591,7 @@ static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, c
         GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    k_edge_bwd_wg<FIRST, NODE, X3><<<grid, BG_N * BG_T, smem, st>>>(te, tm, tde, tout, tdpj, tdpj8, a);
+    launch_k(k_edge_bwd_wg<FIRST, NODE, X3>, dim3(grid), dim3(BG_N * BG_T), smem, st, te, tm, tde, tout, tdpj, tdpj8, a);
     return GCRL_OK;
 }
 

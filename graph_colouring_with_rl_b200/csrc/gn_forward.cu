@@ -53,6 +53,7 @@ struct EdgeArgs {
 
 template <bool FIRST>
 __global__ void __launch_bounds__(256, 2) k_edge_fwd(const EdgeArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EdgeSmem& S = *reinterpret_cast<EdgeSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256, 2) k_edge_fwd(const EdgeArgs a) {
 __global__ void k_node_proj_first(const float* __restrict__ x, int Dv, const float* __restrict__ W1,
                                   int ldW1, const float* __restrict__ b1, int64_t N,
                                   float* __restrict__ Pi, float* __restrict__ Pj) {
+    pdl_prologue();
     int64_t total = N * 64;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -245,6 +247,7 @@ __host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
 
 template <bool LAST>
 __global__ void __launch_bounds__(256, 1) k_node_update(const NodeArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(16) float smem_f[];
     const int K1 = 256 + a.Dv;
     const int ld_in = round4(K1) + 4;
@@ -399,8 +402,8 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
     int64_t grid = (int64_t)sm_count() * 2;
     if (grid > items) grid = items;
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_FWD_FIRST : (m_out ? GCRL_PROF_EDGE_FWD : GCRL_PROF_EDGE_FWD_LAST), st);
-    if (first) k_edge_fwd<true><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
-    else k_edge_fwd<false><<<(int)grid, 256, sizeof(EdgeSmem), st>>>(a);
+    if (first) launch_k(k_edge_fwd<true>, dim3((int)grid), dim3(256), sizeof(EdgeSmem), st, a);
+    else launch_k(k_edge_fwd<false>, dim3((int)grid), dim3(256), sizeof(EdgeSmem), st, a);
     prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
@@ -451,8 +454,8 @@ int launch_node_update(const NetW& net, int l /*0-based*/, bool with_extra, cons
     int64_t tiles = (N + TV - 1) / TV;
     int64_t grid = sm_count();
     if (grid > tiles) grid = tiles;
-    if (last) k_node_update<true><<<(int)grid, 256, smem, st>>>(a);
-    else k_node_update<false><<<(int)grid, 256, smem, st>>>(a);
+    if (last) launch_k(k_node_update<true>, dim3((int)grid), dim3(256), smem, st, a);
+    else launch_k(k_node_update<false>, dim3((int)grid), dim3(256), smem, st, a);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -524,7 +527,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         int64_t total = N * 64;
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N,
+        launch_k(k_node_proj_first, dim3((int)blocks), dim3(256), 0, st, x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N,
                                                        stash_p ? S.Pi[0] : Pi, stash_p ? S.Pj[0] : Pj);
         GCRL_LAUNCH_CHECK();
     }
@@ -595,7 +598,7 @@ int gcrl_gn_block_forward(const float* params, int vdim, int edim, int gdim, int
         int64_t total = N * 64;
         int64_t blocks = (total + 255) / 256;
         if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
-        k_node_proj_first<<<(int)blocks, 256, 0, st>>>(x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
+        launch_k(k_node_proj_first, dim3((int)blocks), dim3(256), 0, st, x, b.Dv, b.W1, 2 * b.Dv + b.De, b.b1, N, Pi, Pj);
         GCRL_LAUNCH_CHECK();
     }
     rc = launch_edge_fwd_mode(math_mode, b, b.De != 64 || block == 1, Pi, Pj, eattr, seg_off, src, dst, N, E, msg_out,

@@ -62,6 +62,7 @@ struct FwdWgArgs {
 template <bool FIRST, bool X3, bool ARG>
 __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_out, const FwdWgArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FwdWgSmem& S = *reinterpret_cast<FwdWgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, wg = tid >> 7, lt = tid & 127, w = lt >> 5, lane = tid & 31;
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
     const int64_t IE = a.item_edges;
     const int64_t n_items = ((int64_t)a.E + IE - 1) / IE;
     for (int64_t it = (int64_t)blockIdx.x * WG_N + wg; it < n_items; it += (int64_t)gridDim.x * WG_N) {
-        const int32_t v0 = seg_lower_bound(a.seg_off, a.N, it * IE);
-        const int32_t v1 = (it + 1 == n_items) ? a.N : seg_lower_bound(a.seg_off, a.N, (it + 1) * IE);
+        int32_t v0, v1;
+        seg_lower_bound2_warp(a.seg_off, a.N, it * IE, (it + 1) * IE, lane, v0, v1);
+        if (it + 1 == n_items) v1 = a.N;
         const int32_t e0 = a.seg_off[v0], e1 = a.seg_off[v1];
         Carry carry;
         carry.dst = -1;
@@ -322,7 +324,7 @@ static int launch_wg_variant(const CUtensorMap& tin, const CUtensorMap& tout, co
         GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd_wg<FIRST, X3, ARG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    k_edge_fwd_wg<FIRST, X3, ARG><<<grid, WG_THREADS, smem, st>>>(tin, tout, a);
+    launch_k(k_edge_fwd_wg<FIRST, X3, ARG>, dim3(grid), dim3(WG_THREADS), smem, st, tin, tout, a);
     return GCRL_OK;
 }
 

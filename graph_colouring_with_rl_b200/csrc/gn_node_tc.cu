@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
                                                         const __grid_constant__ CUtensorMap tm2,
                                                         const __grid_constant__ CUtensorMap tmo0,
                                                         const __grid_constant__ CUtensorMap tmo1, const RowsGemmArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int nch = a.n1 + a.n2;
@@ -222,7 +223,7 @@ static int launch_rows_gemm(const CUtensorMap& t1, const CUtensorMap& t2, const 
     int64_t tiles = (a.N + 127) / 128;
     int64_t grid = sm_count();
     if (grid > tiles) grid = tiles;
-    k_rows_gemm_tc<NOUT, X3><<<(int)grid, 256, smem, st>>>(t1, t2, o0, o1, a);
+    launch_k(k_rows_gemm_tc<NOUT, X3>, dim3((int)grid), dim3(256), smem, st, t1, t2, o0, o1, a);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }
@@ -273,6 +274,7 @@ template <bool X3>
 __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant__ CUtensorMap tmY,
                                                          const __grid_constant__ CUtensorMap tm1,
                                                          const __grid_constant__ CUtensorMap tm2, const RowsWgradArgs a) {
+    pdl_prologue();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* L0 = reinterpret_cast<float*>(base);
@@ -363,6 +365,7 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
 // agg rows of vertices without incoming edges take the scatter defaults (0, 0, 0, sqrt(eps)): the edge kernel never
 // visits them (principal_neighbourhood_aggregation.py:45-64 on an empty segment)
 __global__ void k_fix_empty_agg(float* __restrict__ agg, const int32_t* __restrict__ seg_off, int64_t N) {
+    pdl_prologue();
     const int64_t total = N * 64;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = t >> 6;
@@ -377,6 +380,7 @@ __global__ void k_fix_empty_agg(float* __restrict__ agg, const int32_t* __restri
 // q[v] = y2[v, :] . F3 + f3
 __global__ void k_head_dot(const float* __restrict__ y2, const float* __restrict__ F3, const float* __restrict__ f3,
                            int64_t N, float* __restrict__ q) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -401,7 +405,7 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
     {
         int64_t blocks = (N * 64 + 255) / 256;
         if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-        k_fix_empty_agg<<<(int)blocks, 256, 0, st>>>(agg, seg_off, N);
+        launch_k(k_fix_empty_agg, dim3((int)blocks), dim3(256), 0, st, agg, seg_off, N);
         GCRL_LAUNCH_CHECK();
     }
     CUtensorMap t_agg, t_h, t_u1, t_ho, t_pi, t_pj, t_y1, t_y2;
@@ -448,7 +452,7 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
     {
         int64_t blocks = (N * 32 + 255) / 256;
         if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
-        k_head_dot<<<(int)blocks, 256, 0, st>>>(y2_buf, net.head.F3, net.head.f3, N, q);
+        launch_k(k_head_dot, dim3((int)blocks), dim3(256), 0, st, y2_buf, net.head.F3, net.head.f3, N, q);
         GCRL_LAUNCH_CHECK();
     }
     return GCRL_OK;
@@ -493,8 +497,8 @@ int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const 
     int64_t tiles = (N + 127) / 128;
     int64_t grid = sm_count();
     if (grid > tiles) grid = tiles;
-    if (x3) k_rows_wgrad_tc<true><<<(int)grid, 256, smem, st>>>(ty, t1, t2, a);
-    else k_rows_wgrad_tc<false><<<(int)grid, 256, smem, st>>>(ty, t1, t2, a);
+    if (x3) launch_k(k_rows_wgrad_tc<true>, dim3((int)grid), dim3(256), smem, st, ty, t1, t2, a);
+    else launch_k(k_rows_wgrad_tc<false>, dim3((int)grid), dim3(256), smem, st, ty, t1, t2, a);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -26,6 +26,7 @@ int sm_count() {
 // ---- in-degree histogram ---------------------------------------------------------------
 __global__ void k_count_deg(const int64_t* __restrict__ ei, int64_t E, int64_t N,
                             int32_t* __restrict__ deg, int32_t* __restrict__ err) {
+    pdl_prologue();
     for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < E;
          k += (int64_t)gridDim.x * blockDim.x) {
         int64_t s = ei[k], d = ei[E + k];
@@ -41,6 +42,7 @@ __global__ void k_count_deg(const int64_t* __restrict__ ei, int64_t E, int64_t N
 // n <= a few million vertices; one CTA of 1024 threads walks 4096-element chunks.
 __global__ void __launch_bounds__(1024) k_exclusive_scan(const int32_t* __restrict__ in,
                                                          int32_t* __restrict__ out, int64_t n) {
+    pdl_prologue();
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t carry_s;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -89,6 +91,7 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int32_t* __restri
 __global__ void k_scatter_ids(const int64_t* __restrict__ ei, int64_t E, int64_t N,
                               const int32_t* __restrict__ seg_off, int32_t* __restrict__ cursor,
                               int32_t* __restrict__ tmp) {
+    pdl_prologue();
     for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < E;
          k += (int64_t)gridDim.x * blockDim.x) {
         int64_t s = ei[k], d = ei[E + k];
@@ -104,6 +107,7 @@ __global__ void k_rank_in_segment(const int64_t* __restrict__ ei, int64_t E,
                                   const int32_t* __restrict__ tmp, int64_t N,
                                   int32_t* __restrict__ src, int32_t* __restrict__ dst,
                                   int32_t* __restrict__ perm) {
+    pdl_prologue();
     const int32_t total = seg_off[N];  // edges with valid ids (all of them unless err is set)
     for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < total;
          s += (int64_t)gridDim.x * blockDim.x) {
@@ -122,6 +126,7 @@ __global__ void k_rank_in_segment(const int64_t* __restrict__ ei, int64_t E,
 // ---- dense complete-graph batches -------------------------------------------------------
 __global__ void k_graph_edge_counts(const int32_t* __restrict__ node_off, int32_t G,
                                     int32_t* __restrict__ cnt) {
+    pdl_prologue();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < G) {
         int32_t n = node_off[g + 1] - node_off[g];
@@ -136,6 +141,7 @@ __global__ void k_pack_dense(const uint8_t* __restrict__ adj, const int64_t* __r
                              int32_t* __restrict__ seg_off, int32_t* __restrict__ src,
                              int32_t* __restrict__ dst, int32_t* __restrict__ perm,
                              float* __restrict__ eattr) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -174,6 +180,7 @@ __global__ void k_pack_dense(const uint8_t* __restrict__ adj, const int64_t* __r
 __global__ void k_permute_rows(const float* __restrict__ in, float* __restrict__ out,
                                const int32_t* __restrict__ perm, int64_t rows, int32_t width,
                                int to_internal) {
+    pdl_prologue();
     int64_t total = rows * width;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -244,13 +251,13 @@ int gcrl_pack(const int64_t* ei, int64_t E, int64_t N, int32_t* seg_off, int32_t
     int blocks = (int)((E + threads - 1) / threads);
     if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     if (blocks < 1) blocks = 1;
-    if (E > 0) k_count_deg<<<blocks, threads, 0, st>>>(ei, E, N, deg, err);
-    k_exclusive_scan<<<1, 1024, 0, st>>>(deg, seg_off, N);
+    if (E > 0) launch_k(k_count_deg, dim3(blocks), dim3(threads), 0, st, ei, E, N, deg, err);
+    launch_k(k_exclusive_scan, dim3(1), dim3(1024), 0, st, deg, seg_off, N);
     if (E > 0) {
-        k_scatter_ids<<<blocks, threads, 0, st>>>(ei, E, N, seg_off, cursor, tmp);
+        launch_k(k_scatter_ids, dim3(blocks), dim3(threads), 0, st, ei, E, N, seg_off, cursor, tmp);
         // edges with invalid ids are dropped (err flag set); ranking walks only the
         // seg_off[N] valid slots, a bound it reads on the device.
-        k_rank_in_segment<<<blocks, threads, 0, st>>>(ei, E, seg_off, tmp, N, src, dst, perm);
+        launch_k(k_rank_in_segment, dim3(blocks), dim3(threads), 0, st, ei, E, seg_off, tmp, N, src, dst, perm);
         count_launch(3);
     }
     GCRL_LAUNCH_CHECK();
@@ -273,13 +280,13 @@ int gcrl_pack_dense(const uint8_t* adj, const int64_t* adj_off, const int32_t* n
     Arena ar(ws, ws_bytes);
     int32_t* cnt = ar.take<int32_t>(G + 2);
     int32_t* eoff = ar.take<int32_t>(G + 2);
-    if (G > 0) k_graph_edge_counts<<<(G + 255) / 256, 256, 0, st>>>(node_off, G, cnt);
-    k_exclusive_scan<<<1, 1024, 0, st>>>(cnt, eoff, G);
+    if (G > 0) launch_k(k_graph_edge_counts, dim3((G + 255) / 256), dim3(256), 0, st, node_off, G, cnt);
+    launch_k(k_exclusive_scan, dim3(1), dim3(1024), 0, st, cnt, eoff, G);
     if (N == 0) GCRL_CUDA(cudaMemsetAsync(seg_off, 0, 4, st));
     if (N > 0) {
         int blocks = (int)((N * 32 + 255) / 256);
         if (blocks > sm_count() * 32) blocks = sm_count() * 32;
-        k_pack_dense<<<blocks, 256, 0, st>>>(adj, adj_off, node_off, eoff, G, N, seg_off, src, dst,
+        launch_k(k_pack_dense, dim3(blocks), dim3(256), 0, st, adj, adj_off, node_off, eoff, G, N, seg_off, src, dst,
                                              perm, eattr);
         count_launch(G > 0 ? 2 : 1);
     }
@@ -295,7 +302,7 @@ int gcrl_permute_rows(const float* in, float* out, const int32_t* perm, int64_t 
     int64_t total = rows * width;
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 32) blocks = sm_count() * 32;
-    k_permute_rows<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, perm, rows, width, to_internal);
+    launch_k(k_permute_rows, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, in, out, perm, rows, width, to_internal);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) k_pna_fwd_w64(const float* __restrict__ m
                                                     int32_t* __restrict__ arg_min,
                                                     int32_t* __restrict__ arg_max,
                                                     float* __restrict__ var_out) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const int half = lane >> 4;         // 0: even rows, 1: odd rows
     const int c4 = (lane & 15);         // float4 column
@@ -139,6 +140,7 @@ __global__ void k_pna_fwd_generic(const float* __restrict__ msg, const int32_t* 
                                   int64_t N, int32_t F, float* __restrict__ out,
                                   int32_t* __restrict__ arg_min, int32_t* __restrict__ arg_max,
                                   float* __restrict__ var_out) {
+    pdl_prologue();
     int64_t total = N * F;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -160,6 +162,7 @@ __global__ void k_pna_fwd_generic(const float* __restrict__ msg, const int32_t* 
 
 __global__ void k_segment_reduce(const float* __restrict__ msg, const int32_t* __restrict__ seg_off,
                                  int64_t N, int32_t F, int which, float* __restrict__ out) {
+    pdl_prologue();
     int64_t total = N * F;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -193,6 +196,7 @@ __global__ void k_pna_bwd(const float* __restrict__ msg, const float* __restrict
                           const int32_t* __restrict__ seg_off, const int32_t* __restrict__ dst,
                           const int32_t* __restrict__ arg_min, const int32_t* __restrict__ arg_max,
                           int64_t E, int32_t F, float* __restrict__ d_msg) {
+    pdl_prologue();
     int64_t total = E * F;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -231,13 +235,13 @@ int gcrl_pna_forward(const float* msg, const int32_t* seg_off, int64_t N, int64_
         int64_t blocks = (N + 7) / 8;
         int64_t cap = (int64_t)sm_count() * 8 * 4;
         if (blocks > cap) blocks = cap;
-        k_pna_fwd_w64<<<(int)blocks, 256, 0, st>>>(msg, seg_off, N, out, arg_min, arg_max, var_out);
+        launch_k(k_pna_fwd_w64, dim3((int)blocks), dim3(256), 0, st, msg, seg_off, N, out, arg_min, arg_max, var_out);
     } else {
         int64_t total = N * F;
         int64_t blocks = (total + 255) / 256;
         int64_t cap = (int64_t)sm_count() * 32;
         if (blocks > cap) blocks = cap;
-        k_pna_fwd_generic<<<(int)blocks, 256, 0, st>>>(msg, seg_off, N, F, out, arg_min, arg_max, var_out);
+        launch_k(k_pna_fwd_generic, dim3((int)blocks), dim3(256), 0, st, msg, seg_off, N, F, out, arg_min, arg_max, var_out);
     }
     prof_end(tok, st);
     GCRL_LAUNCH_CHECK();
@@ -256,7 +260,7 @@ int gcrl_pna_backward(const float* msg, const float* out, const float* var, cons
     int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
     const int tok = prof_begin(GCRL_PROF_PNA_BWD, (cudaStream_t)stream);
-    k_pna_bwd<1><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(msg, out, var, d_out, seg_off, dst,
+    launch_k(k_pna_bwd<1>, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, msg, out, var, d_out, seg_off, dst,
                                                               arg_min, arg_max, E, F, d_msg);
     prof_end(tok, (cudaStream_t)stream);
     GCRL_LAUNCH_CHECK();
@@ -272,7 +276,7 @@ int gcrl_segment_reduce(const float* msg, const int32_t* seg_off, int64_t N, int
     int64_t blocks = (total + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    k_segment_reduce<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(msg, seg_off, N, F, which, out);
+    launch_k(k_segment_reduce, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, msg, seg_off, N, F, which, out);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

@@ -15,6 +15,15 @@ static std::mutex g_mu;
 
 void count_launch(int n) { g_launches += n; }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GCRL_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
     cudaEvent_t e = nullptr;

@@ -185,7 +185,7 @@ def gn_block_forward(params, dims, block, packed, x, eattr, math_mode=_lib.GCRL_
 
 
 def gn_backward(params, dims, packed, x, eattr, stash, d_q=None, d_h=None, gfeat=None, vgraph=None,
-                grad=None, accumulate=False, math_mode=_lib.GCRL_MATH_FP32):
+                grad=None, accumulate=False, math_mode=_lib.GCRL_MATH_FP32, ws=None):
     """Returns the flat gradient [P] (written into `grad` when given)."""
     lib = _lib.load()
     dev = params.device
@@ -193,7 +193,9 @@ def gn_backward(params, dims, packed, x, eattr, stash, d_q=None, d_h=None, gfeat
     if grad is None:
         grad = torch.empty_like(params)
         accumulate = False
-    ws = workspace(lib.gcrl_gn_backward_workspace_bytes(N, E), dev, 'gnbwd')
+    nb_ws = lib.gcrl_gn_backward_workspace_bytes(N, E)
+    if ws is None or ws.numel() < nb_ws:
+        ws = workspace(nb_ws, dev, 'gnbwd')
     d_q = d_q.contiguous() if d_q is not None else None
     d_h = d_h.contiguous() if d_h is not None else None
     with torch.cuda.device(dev):

@@ -37,6 +37,14 @@ class TransitionBatch(object):
         self.names = (torch.arange(self.n_vertices, device=dev) - start).float()   # x[:,0] (graph_colouring_env.py:124-128)
 
     @classmethod
+    def empty(cls, device):
+        """A minibatch without graphs (a rank whose replay ring is still empty joins the collective with this)."""
+        dev = torch.device(device)
+        z = lambda dt: torch.zeros(0, dtype=dt, device=dev)
+        return cls(np.zeros(0, dtype=np.int64), z(torch.uint8), z(torch.int32), z(torch.int32), z(torch.int32), z(torch.float32),
+                   z(torch.int32))
+
+    @classmethod
     def from_host(cls, ns, host, device):
         """host: dict of (ideally pinned) CPU tensors named like FIELDS; async H2D copies."""
         dev = torch.device(device)

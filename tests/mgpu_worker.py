@@ -29,8 +29,57 @@ def er(n, p, rng):
     return a | a.T
 
 
+def train_main():
+    """Multi-GPU DeviceTrainer (dqn_main.py:158-199 sharded by graph): after 3 waves of 16 episodes on 2 ranks the
+    replicas hold bit-identical parameters, both ranks took the same number of learn steps, the learn cadence matches
+    the global environment-step count, and the gathered statistics cover every episode."""
+    out_dir = sys.argv[1]
+    rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    os.environ['GCRL_DEVICE'] = 'cuda:%d' % local
+    dist.init_process_group('nccl', device_id=dev)
+    from graph_colouring_with_rl_b200.dqn_agent import DQNAgentGN
+    from graph_colouring_with_rl_b200.dqn_main import DeviceTrainer
+    rng = np.random.default_rng(5)
+    graphs = [er(int(n), 0.5, rng) for n in rng.integers(12, 31, size=24)]
+    val = [dict(adj=er(int(n), 0.4, rng), name='v%d' % i) for i, n in enumerate(rng.integers(10, 25, size=7))]
+    torch.manual_seed(50 + rank)                      # different seeds: the learner's broadcast makes the replicas equal
+    np.random.seed(3 + rank)
+    agent = DQNAgentGN(2, 1, 0, math_mode='bf16x3')
+    agent.batch_size = 16                             # gate = 160 stored transitions: reached in the second wave
+    tr = DeviceTrainer(agent, graphs, val, n_envs=16, device_seed=1, validate_every=32, distributed=True)
+    assert tr.world == world and tr.rank == rank
+    tr.run(48, verbose=False)
+    assert tr.episodes_done == 48 and len(tr.training_stats.colours_used) == 48
+    n_learn = torch.tensor([len(tr.losses), tr.t_step], device=dev)
+    both = [torch.empty_like(n_learn) for _ in range(world)]
+    dist.all_gather(both, n_learn)
+    assert all(torch.equal(b, both[0]) for b in both), both
+    assert len(tr.losses) > 0, 'the gate was never passed'
+    assert all(np.isfinite(float(l.item())) for l in tr.losses)
+    for net in (agent.gn_behaviour, agent.gn_target):
+        p = net.flat_params()
+        parts = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(parts, p.contiguous())
+        assert all(torch.equal(q, parts[0]) for q in parts), 'replicas diverged'
+    # validation ran at episodes 0, 32 on every rank with the same gathered result
+    assert sorted(tr.all_validation_stats.keys()) == [0, 32]
+    assert len(tr.all_validation_stats[32].colours_used) == len(val)
+    if rank == 0:
+        with open(os.path.join(out_dir, 'mgpu_train_rank0.json'), 'w') as f:
+            json.dump({'world': world, 'episodes': tr.episodes_done, 'env_steps': tr.t_step, 'learn_steps': len(tr.losses),
+                       'last_loss': float(tr.losses[-1].item()), 'mean_colours_last16': float(np.mean(tr.training_stats.colours_used[-16:])),
+                       'validation_colours_ep32': float(np.mean(tr.all_validation_stats[32].colours_used))}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     out_dir, math_mode = sys.argv[1], sys.argv[2]
+    if math_mode == 'train':
+        return train_main()
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
