@@ -149,7 +149,7 @@ class FusedAdam(torch.optim.Optimizer):
         if g is None or g.device != flat.device:
             g = net._flat_grad = torch.zeros_like(flat)
         base = g.data_ptr()
-        for p, off in zip(net.parameters(), net._offsets):
+        for p, off in zip(net._param_list(), net._offsets):
             if p.grad is None:
                 g[off:off + p.numel()].zero_()
             elif p.grad.data_ptr() != base + 4 * off:
@@ -207,7 +207,7 @@ class _GNFunction(torch.autograd.Function):
                                d_q=None if d_q is None else d_q.reshape(-1).float(),
                                d_h=None if d_h is None else d_h.float(), gfeat=ctx.gfeat, vgraph=ctx.vgraph,
                                math_mode=net.math_mode)
-        views = tuple(grad[off:off + p.numel()].view(p.shape) for p, off in zip(net.parameters(), net._offsets))
+        views = tuple(grad[off:off + p.numel()].view(p.shape) for p, off in zip(net._param_list(), net._offsets))
         return (None, None, None, None, None, None) + views
 
 
@@ -243,10 +243,20 @@ class GNNetwork(nn.Module):
         self.optimizer = FusedAdam(self, lr=alpha)       # :173
 
     # ---- flat parameter buffer ------------------------------------------------------------
+    def _param_list(self):
+        """The 46 parameters in state_dict order, cached: nn.Module.parameters() walks the module tree (~0.1 ms), and the
+        hot loops ask for the flat buffer several times per step.  The Parameter OBJECTS never change (load_state_dict,
+        .to() and optimizers rewrite their .data), so the list stays valid; flat_params() re-checks the storages."""
+        pl = self.__dict__.get('_params_cached')
+        if pl is None:
+            pl = list(self.parameters())
+            self.__dict__['_params_cached'] = pl
+        return pl
+
     def flat_params(self):
         """The [198 529] fp32 buffer all parameters alias.  Rebuilt (and the parameters
         re-pointed) if anything replaced a parameter's storage, e.g. `.to()` or `.data = ...`."""
-        params = list(self.parameters())
+        params = self._param_list()
         flat = self._flat
         if flat is not None:
             base = flat.data_ptr()
@@ -282,7 +292,7 @@ class GNNetwork(nn.Module):
         """-> (vertex_embeddings [N,64], q_values [N,1]) (architecture.py:179-199).
         `edge_batch_map` and `called_by` are accepted and unused, as in the reference."""
         x, packed, eattr_i, gfeat, vgraph = self._prepare(data, global_features, vertex_batch_map)
-        params = list(self.parameters())
+        params = self._param_list()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _GNFunction.apply(self, packed, x, eattr_i, gfeat, vgraph, *params)
         h, q, _ = ops.gn_forward(self.flat_params(), self.dims, packed, x, eattr_i, gfeat, vgraph,

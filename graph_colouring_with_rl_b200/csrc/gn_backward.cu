@@ -108,7 +108,7 @@ static int launch_gemm(GemmArgs g, cudaStream_t st) {
         if (want < 1) want = 1;
         int64_t chunk = (g.K + want - 1) / want;
         chunk = (chunk + GK - 1) / GK * GK;
-        if (chunk < 256) chunk = 256;
+        if (chunk < 64) chunk = 64;          // each CTA's K loop is a chain of dependent global-load rounds: keep it short
         g.k_chunk = chunk;
     } else {
         g.k_chunk = g.K > 0 ? g.K : 1;
@@ -528,9 +528,34 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
 // gn_node_tc.cu: vertex-side products on the tensor cores
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
-               int accumulate, int64_t N, cudaStream_t st);
+               int accumulate, int64_t N, cudaStream_t st, const float* dY2 = nullptr, int ngroups = 1);
 int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
-               int gcol0, int64_t N, cudaStream_t st);
+               int gcol0, float* gbias, int64_t N, cudaStream_t st);
+
+// first stage of the head's backward (architecture.py:197 fc3 and the ReLU in front of it) in one launch:
+//   dy2[r][k] = dq[r] F3[k] [y2[r][k] > 0],   gF3[k] += sum_r dq[r] y2[r][k],   gf3 += sum_r dq[r]
+__global__ void __launch_bounds__(256) k_head_bwd_first(const float* __restrict__ dq, const float* __restrict__ y2,
+                                                       const float* __restrict__ F3, int64_t N, float* __restrict__ dy2,
+                                                       float* __restrict__ gF3, float* __restrict__ gf3) {
+    pdl_prologue();
+    __shared__ float part[4][65];
+    const int c = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const float w = F3[c];
+    float s = 0.f, sb = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * 4 + q; r < N; r += (int64_t)gridDim.x * 4) {
+        const float g = dq[r], y = y2[r * 64 + c];
+        dy2[r * 64 + c] = y > 0.f ? g * w : 0.f;
+        s = fmaf(g, y, s);
+        sb += g;
+    }
+    part[q][c] = s;
+    if (c == 0) part[q][64] = sb;
+    __syncthreads();
+    if (q == 0) {
+        atomicAdd(&gF3[c], (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]));
+        if (c == 0) atomicAdd(gf3, (part[0][64] + part[1][64]) + (part[2][64] + part[3][64]));
+    }
+}
 
 
 }  // namespace gcrl
@@ -593,6 +618,20 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
     if (d_q) {
         float* dy2 = du1;       // reuse
         float* dy1 = scratch;
+        static const bool node_ffma_h = getenv("GCRL_NODE_IMPL") && getenv("GCRL_NODE_IMPL")[0] == 'f';
+        if (math_mode != GCRL_MATH_FP32 && !node_ffma_h && hd.Dg == 0) {
+            // tensor-core modes: the 64-wide products of the head on tcgen05 like the blocks' vertex side, bias gradients
+            // fused into the weight-gradient kernels, fc3's three tiny products in one launch (12 launches -> 5)
+            const bool x3h = math_mode == GCRL_MATH_BF16X3;
+            int64_t blocks = (N + 3) / 4;
+            if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
+            launch_k(k_head_bwd_first, dim3((int)blocks), dim3(256), 0, st, d_q, S.y2, hd.F3, N, dy2, G(hd.F3), G(hd.f3));
+            GCRL_LAUNCH_CHECK();
+            RC(wgrad64_tc(x3h, dy2, S.y1, 64, 1, nullptr, 0, 0, G(hd.F2), 64, 0, G(hd.f2), N, st));
+            RC(dgrad64_tc(x3h, dy2, hd.F2, 64, 0, dy1, 64, 0, S.y1, 0, N, st));
+            RC(wgrad64_tc(x3h, dy1, h5, 64, 1, nullptr, 0, 0, G(hd.F1), 64, 0, G(hd.f1), N, st));
+            RC(dgrad64_tc(x3h, dy1, hd.F1, 64, 0, dh, 64, 0, nullptr, 0, N, st));
+        } else {
         RC(wgrad(d_q, 1, 1, S.y2, 64, 64, G(hd.F3), 64, 0, N, st));              // dF3
         RC(colsum(d_q, N, 1, G(hd.f3), st));                                     // df3
         RC(dgrad(d_q, 1, 1, hd.F3, 64, 0, 64, dy2, 64, S.y2, 0, N, st));         // dy2 = dq F3 * relu'
@@ -611,6 +650,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         }
         RC(colsum(dy1, N, 64, G(hd.f1), st));
         RC(dgrad(dy1, 64, 64, hd.F1, ldF1, 0, 64, dh, 64, nullptr, 0, N, st));   // dh5
+        }
         if (d_h) {
             int64_t n = N * 64;
             int blocks = (int)((n + 255) / 256);
@@ -636,13 +676,12 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         const bool vtc = math_mode != GCRL_MATH_FP32 && !node_ffma;
         const bool x3 = math_mode == GCRL_MATH_BF16X3;
         if (vtc) {
-            RC(wgrad64_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, N, st));
-            RC(colsum(dh, N, 64, G(b.c2), st));
+            // bias gradients ride in the weight-gradient launches; d agg's four 64-column windows are one launch
+            RC(wgrad64_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, G(b.c2), N, st));
             RC(dgrad64_tc(x3, dh, b.U2, 64, 0, du1, 64, 0, S.u1[l], 0, N, st));
-            RC(wgrad64_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, b.Dv == 64 ? 1 : 0, G(b.U1), ldU1, 0, N, st));
+            RC(wgrad64_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, b.Dv == 64 ? 1 : 0, G(b.U1), ldU1, 0, G(b.c1), N, st));
             if (b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
-            RC(colsum(du1, N, 64, G(b.c1), st));
-            for (int c = 0; c < 4; ++c) RC(dgrad64_tc(x3, du1, b.U1, ldU1, 64 * c, dagg, 256, 64 * c, nullptr, 0, N, st));
+            RC(dgrad64_tc(x3, du1, b.U1, ldU1, 0, dagg, 256, 0, nullptr, 0, N, st, nullptr, 4));
             if (l > 0) RC(dgrad64_tc(x3, du1, b.U1, ldU1, 256, dh_prev, 64, 0, nullptr, 0, N, st));
         } else {
         RC(wgrad(dh, 64, 64, S.u1[l], 64, 64, G(b.U2), 64, 0, N, st));
@@ -655,8 +694,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         if (l > 0) RC(dgrad(du1, 64, 64, b.U1, ldU1, 256, 64, dh_prev, 64, nullptr, 0, N, st));
         }
         // message MLP + aggregation (architecture.py:51-66)
-        GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)N * 64 * 4, st));
-        GCRL_CUDA(cudaMemsetAsync(dPj, 0, (size_t)N * 64 * 4, st));
+        GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)(dPj - dPi) * 4 + (size_t)N * 64 * 4, st));     // dPi and dPj are adjacent
         float* de_prev = (l > 0) ? deb[l & 1] : nullptr;
         const bool tc_ok = (l == 0) ? (b.De <= 8) : (b.De == 64);
         if (E > 0 && math_mode != GCRL_MATH_FP32 && tc_ok) {
@@ -687,16 +725,16 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         }
         // vertex columns of message_mlp.0: Pi = A h + b1, Pj = B h
         if (vtc && b.Dv == 64) {
-            RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, N, st));
-            RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, N, st));
+            RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), N, st));
+            RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, N, st));
         } else {
             RC(wgrad(dPi, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, 0, N, st));
             RC(wgrad(dPj, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, b.Dv, N, st));
+            RC(colsum(dPi, N, 64, G(b.b1), st));
         }
-        RC(colsum(dPi, N, 64, G(b.b1), st));
         if (l > 0 && vtc) {
-            RC(dgrad64_tc(x3, dPi, b.W1, ldW1, 0, dh_prev, 64, 0, nullptr, 1, N, st));
-            RC(dgrad64_tc(x3, dPj, b.W1, ldW1, 64, dh_prev, 64, 0, nullptr, 1, N, st));
+            // dh_{l-1} += dPi A + dPj B: two K chunks of one launch
+            RC(dgrad64_tc(x3, dPi, b.W1, ldW1, 0, dh_prev, 64, 0, nullptr, 1, N, st, dPj));
             float* t = dh; dh = dh_prev; dh_prev = t;
         } else if (l > 0) {
             RC(dgrad(dPi, 64, 64, b.W1, ldW1, 0, 64, dh_prev, 64, nullptr, 1, N, st));

@@ -465,6 +465,11 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
                           const int32_t* seg_off, int64_t N, float* h_out, float* Pi, float* Pj, float* q,
                           float* u1_buf, float* y1_buf, float* y2_buf, cudaStream_t st);
 
+// gn_vertex_fwd.cu: the same vertex side as ONE launch per block (default; GCRL_VERTEX_IMPL=split keeps the launch chain)
+int launch_vertex_fwd_fused(const NetW& net, int l, bool x3, float* agg, const float* h_in, const int32_t* seg_off, int64_t N,
+                            float* h_out, float* Pi, float* Pj, float* q, float* u1_buf, float* y1_buf, float* y2_buf, bool stash,
+                            cudaStream_t st);
+
 }  // namespace gcrl
 
 using namespace gcrl;
@@ -554,6 +559,12 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         static const bool node_ffma = getenv("GCRL_NODE_IMPL") && getenv("GCRL_NODE_IMPL")[0] == 'f';   // A/B switch
         if (math_mode != GCRL_MATH_FP32 && gdim == 0 && (Dv_l == 64 || Dv_l <= 8) && !node_ffma) {
             // tensor-core vertex side; without a stash the (dead) projection buffers of this block serve as scratch
+            static const bool vertex_split = getenv("GCRL_VERTEX_IMPL") && getenv("GCRL_VERTEX_IMPL")[0] == 's';   // A/B switch
+            if (!vertex_split)
+                rc = launch_vertex_fwd_fused(net, l, math_mode == GCRL_MATH_BF16X3, agg, h_prev, seg_off, N, hl, Pin, Pjn, q_out,
+                                             stash_p ? S.u1[l] : nullptr, stash_p ? S.y1 : nullptr, stash_p ? S.y2 : nullptr,
+                                             stash_p != nullptr, st);
+            else
             rc = launch_node_update_tc(net, l, true, math_mode == GCRL_MATH_BF16X3, agg, h_prev, seg_off, N, hl, Pin, Pjn, q_out,
                                        stash_p ? S.u1[l] : Pi, stash_p ? S.y1 : Pi, stash_p ? S.y2 : Pj, st);
         } else

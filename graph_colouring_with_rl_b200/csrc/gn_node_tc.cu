@@ -24,7 +24,10 @@ struct RowsGemmArgs {
     int n1, n2;                            // 64-column chunks taken from tensor map 1 / tensor map 2
     const float* xt; int Dt;               // tail: out0[:, o] += sum_{d < Dt} Wt[o * ldWt + colt + d] * xt[row * Dt + d]
     const float* Wt; int ldWt, colt;
-    int wT;                                // weights read transposed: element (o, k) = W[k * ldW + col + o]   (dgrad: dX = dY W)
+    int wT;                                // weights read transposed: element (o, k) = W[k * ldW + col + o]   (dgrad: dX = dY W);
+                                           // K chunk c then takes the window col0 + 64 c (dX = dY_0 W[:, w_0] + dY_1 W[:, w_1] ...)
+    int ngroups;                           // wT, one K chunk, NOUT = 64: output group g = dY W[:, col0 + 64 g : +64] goes to output
+                                           // columns ocol0 + 64 g (one operand conversion, ngroups products; <= NODE_MAX_CHUNKS)
     int ocol0, ocol1;                      // column offsets of the two outputs inside their [N, ld] matrices
     const float* mask; int ldmask;         // out0[r][o] *= (mask[r * ldmask + o] > 0)   (relu' of a stashed activation) or null
     int accumulate;                        // outputs are added to memory (TMA reduce-add) instead of stored
@@ -61,9 +64,11 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int nch = a.n1 + a.n2;
+    const int ngr = a.ngroups > 1 ? a.ngroups : 1;            // weight tiles in shared memory: nch chunks or ngr groups
+    const int nwt = nch > ngr ? nch : ngr;
     constexpr int WCH = (NOUT / 64) * 16384;                  // bytes of one weight chunk: hi [NOUT x 64] | lo [NOUT x 64]
     unsigned char* Wsm = base;                                // [nch][WCH]
-    float* L0 = reinterpret_cast<float*>(base + nch * WCH);   // landing / staging tiles (fp32 SW128 slabs)
+    float* L0 = reinterpret_cast<float*>(base + nwt * WCH);   // landing / staging tiles (fp32 SW128 slabs)
     float* L1 = L0 + 128 * 64;
     unsigned char* Aop = reinterpret_cast<unsigned char*>(L1 + 128 * 64);   // operand tile hi | lo
     float* bias_s = reinterpret_cast<float*>(Aop + 32768);    // [128]
@@ -82,13 +87,13 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
         mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<128>(tmem_slot);
-    for (int c = 0; c < nch; ++c) {
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    for (int c = 0; c < nwt; ++c) {
         __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH);
         __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(Wsm + c * WCH + WCH / 2);
-        if (a.wT) {          // (single K chunk: the contraction runs over the 64 rows of W)
-            load_weight_tile_T(a.W0, a.ldW0, a.col0, hi, lo, tid, 256);
-            if (NOUT == 128) load_weight_tile_T(a.W1, a.ldW1, a.col1, hi + 64 * 64, lo + 64 * 64, tid, 256);
+        if (a.wT) {          // the contraction runs over the 64 rows of W; tile c = window col0 + 64 c (K chunk or output group)
+            load_weight_tile_T(a.W0, a.ldW0, a.col0 + 64 * c, hi, lo, tid, 256);
+            if (NOUT == 128) load_weight_tile_T(a.W1, a.ldW1, a.col1 + 64 * c, hi + 64 * 64, lo + 64 * 64, tid, 256);
         } else {
             load_weight_tile(a.W0, a.ldW0, a.col0 + 64 * c, hi, lo, tid, 256);
             if (NOUT == 128) load_weight_tile(a.W1, a.ldW1, a.col1 + 64 * c, hi + 64 * 64, lo + 64 * 64, tid, 256);
@@ -138,8 +143,15 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
             if (warp == 0 && elect_one()) {
                 if (c + 2 < nch) issue_load(c + 2, v0);
                 tc_fence_after();
-                const uint32_t w_hi = smem_u32(Wsm + c * WCH);
-                issue_gemm_feat<X3>(tmem, smem_u32(Aop), smem_u32(Aop) + 16384, w_hi, w_hi + WCH / 2, idesc, c > 0);
+                if (ngr > 1) {          // one operand, ngr weight windows -> ngr accumulators of 64 columns
+                    for (int g = 0; g < ngr; ++g) {
+                        const uint32_t w_hi = smem_u32(Wsm + g * WCH);
+                        issue_gemm_feat<X3>(tmem + 64 * g, smem_u32(Aop), smem_u32(Aop) + 16384, w_hi, w_hi + WCH / 2, idesc, false);
+                    }
+                } else {
+                    const uint32_t w_hi = smem_u32(Wsm + c * WCH);
+                    issue_gemm_feat<X3>(tmem, smem_u32(Aop), smem_u32(Aop) + 16384, w_hi, w_hi + WCH / 2, idesc, c > 0);
+                }
                 umma_commit(bar_mma);
             }
         }
@@ -152,13 +164,19 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
 #pragma unroll
         for (int d = 0; d < 8; ++d) xt[d] = (valid && d < a.Dt) ? a.xt[(int64_t)(v0 + row) * a.Dt + d] : 0.f;
         constexpr int PASSES = NOUT / 64;               // 32-column passes per warp
+        for (int g = 0; g < ngr; ++g) {                 // output groups (NOUT = 64 only): staging tiles alternate
+        float* Lg = (NOUT == 64 && (g & 1)) ? L1 : L0;
+        if (g >= 2) {                                   // the store of group g - 2 has read this staging tile
+            if (tid == 0) bulk_wait_read1();
+            __syncthreads();
+        }
 #pragma unroll
         for (int p = 0; p < PASSES; ++p) {
             // NOUT = 64: warp half h owns columns [32h, 32h+32); NOUT = 128: half h owns output matrix h, two passes
             const int col0 = NOUT == 64 ? 32 * half : 64 * half + 32 * p;
             float acc[32];
-            tmem_ld32(tmem + lane_addr + col0, acc);
-            float* Lout = (NOUT == 128 && half == 1) ? L1 : L0;
+            tmem_ld32(tmem + lane_addr + col0 + 64 * g, acc);
+            float* Lout = (NOUT == 128 && half == 1) ? L1 : Lg;
             const int lc0 = col0 & 63;                  // column inside the 64-wide staging tile
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -181,30 +199,32 @@ __global__ void __launch_bounds__(256, 1) k_rows_gemm_tc(const __grid_constant__
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
+            const int oc = a.ocol0 + 64 * g;
             if (a.accumulate) {                          // rows past N are clipped by the tensor map
-                tma_reduce_add_2d(&tmo0, a.ocol0, v0, L0);
-                tma_reduce_add_2d(&tmo0, a.ocol0 + 32, v0, L0 + 128 * 32);
+                tma_reduce_add_2d(&tmo0, oc, v0, Lg);
+                tma_reduce_add_2d(&tmo0, oc + 32, v0, Lg + 128 * 32);
                 if (NOUT == 128) {
                     tma_reduce_add_2d(&tmo1, a.ocol1, v0, L1);
                     tma_reduce_add_2d(&tmo1, a.ocol1 + 32, v0, L1 + 128 * 32);
                 }
             } else {
-                tma_store_2d(&tmo0, a.ocol0, v0, L0);
-                tma_store_2d(&tmo0, a.ocol0 + 32, v0, L0 + 128 * 32);
+                tma_store_2d(&tmo0, oc, v0, Lg);
+                tma_store_2d(&tmo0, oc + 32, v0, Lg + 128 * 32);
                 if (NOUT == 128) {
                     tma_store_2d(&tmo1, a.ocol1, v0, L1);
                     tma_store_2d(&tmo1, a.ocol1 + 32, v0, L1 + 128 * 32);
                 }
             }
             bulk_commit();
-            bulk_wait_read0();
+            if (g + 1 == ngr) bulk_wait_read0();
+        }
         }
         __syncthreads();                                 // staging tiles are free for the next tile's loads
     }
     if (tid == 0) bulk_wait0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<128>(tmem);
+    if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
 // host side: tensor map of a row-major fp32 matrix [rows, cols] (cols a multiple of 32), box {32, 128}
@@ -214,7 +234,10 @@ template <int NOUT, bool X3>
 static int launch_rows_gemm(const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& o0, const CUtensorMap& o1,
                             const RowsGemmArgs& a, cudaStream_t st) {
     const int nch = a.n1 + a.n2;
-    const int smem = nch * (NOUT / 64) * 16384 + 2 * 32768 + 32768 + 128 * 4 + 64 * 8 * 4 + 64 + 1024;
+    const int nwt = a.ngroups > nch ? a.ngroups : nch;
+    GCRL_CHECK_ARG(nwt <= NODE_MAX_CHUNKS);
+    GCRL_CHECK_ARG(a.ngroups <= 1 || (NOUT == 64 && a.wT && nch == 1 && !a.bias0 && !a.mask && a.Dt == 0 && !a.relu));
+    const int smem = nwt * (NOUT / 64) * 16384 + 2 * 32768 + 32768 + 128 * 4 + 64 * 8 * 4 + 64 + 1024;
     static int max_set = 0;
     if (smem > max_set) {
         GCRL_CUDA(cudaFuncSetAttribute(k_rows_gemm_tc<NOUT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -260,6 +283,8 @@ static int make_tmap_rows(CUtensorMap* out, const float* basep, int64_t rows, in
     return GCRL_OK;
 }
 
+int make_tmap_rows_pub(CUtensorMap* out, const float* basep, int64_t rows, int cols) { return make_tmap_rows(out, basep, rows, cols); }
+
 // G[o][gcol0 + 64 c + k] += sum_r Y[r][o] X_c[r][k]: weight gradients of the vertex-side Linear layers.  Y [N,64] and the
 // 64-column chunks X_c of up to two [N, 64 n] matrices arrive by TMA; both become bf16 hi/lo operand tiles that are
 // read MN-major (the contraction runs over the 128 rows of a tile); one TMEM accumulator per chunk lives for the
@@ -267,6 +292,7 @@ static int make_tmap_rows(CUtensorMap* out, const float* basep, int64_t rows, in
 struct RowsWgradArgs {
     int n1, n2;
     float* G; int ldG, gcol0;
+    float* gbias;                          // [64] += column sums of Y (the bias gradient of the same Linear layer) or null
     int64_t N;
 };
 
@@ -284,8 +310,11 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
     uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Xop + 32768);      // [2]
     uint64_t* bar_mma = bar_tma + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 3);
+    float* bsum_s = reinterpret_cast<float*>(bar_tma + 4);             // [64] bias-gradient partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nch = a.n1 + a.n2;
+    if (tid < 64) bsum_s[tid] = 0.f;
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);                     // columns 4 (tid & 15) .. +3 over this thread's rows
     if (tid == 0) {
         mbar_init(&bar_tma[0], 1);
         mbar_init(&bar_tma[1], 1);
@@ -323,6 +352,15 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
                 ph_mma ^= 1u;
             }
             unsigned char* dstop = j == 0 ? Yop : Xop;
+            if (j == 0 && a.gbias) {
+                // rows past N arrive as zeros (TMA out-of-bounds fill): they add nothing
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int t = it * 256 + tid;
+                    const float4 v = *reinterpret_cast<const float4*>(l_ptr(L, t >> 4, t & 15));
+                    bacc.x += v.x; bacc.y += v.y; bacc.z += v.z; bacc.w += v.w;
+                }
+            }
             convert_tile128<X3>(L, reinterpret_cast<__nv_bfloat16*>(dstop), reinterpret_cast<__nv_bfloat16*>(dstop + 16384), tid);
             fence_proxy_async();
             __syncthreads();
@@ -357,8 +395,14 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
             }
         }
     }
+    if (a.gbias) {
+        const int c4 = tid & 15;
+        atomicAdd(&bsum_s[4 * c4 + 0], bacc.x); atomicAdd(&bsum_s[4 * c4 + 1], bacc.y);
+        atomicAdd(&bsum_s[4 * c4 + 2], bacc.z); atomicAdd(&bsum_s[4 * c4 + 3], bacc.w);
+    }
     tc_fence_before();
     __syncthreads();
+    if (a.gbias && !first_tile && tid < 64) atomicAdd(&a.gbias[tid], bsum_s[tid]);
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -421,7 +465,7 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
     a.bias0 = b.c1; a.bias1 = nullptr; a.relu = 1;
     a.n1 = 4; a.n2 = wide_h ? 1 : 0;
     a.xt = wide_h ? nullptr : h_in; a.Dt = wide_h ? 0 : b.Dv; a.Wt = b.U1; a.ldWt = K1; a.colt = 256;
-    a.N = N; a.wT = 0; a.ocol0 = 0; a.ocol1 = 0; a.mask = nullptr; a.ldmask = 0; a.accumulate = 0;
+    a.N = N; a.wT = 0; a.ngroups = 1; a.ocol0 = 0; a.ocol1 = 0; a.mask = nullptr; a.ldmask = 0; a.accumulate = 0;
     rc = x3 ? launch_rows_gemm<64, true>(t_agg, t_h, t_u1, t_u1, a, st) : launch_rows_gemm<64, false>(t_agg, t_h, t_u1, t_u1, a, st);
     if (rc) return rc;
     // update_mlp.2
@@ -461,24 +505,27 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
 
 // dX[N, 64] (+)= (dY[N,64] . W[64, wcol : wcol + 64]) * (mask > 0), on the tensor cores.  dX may be a 64-column window
 // (column xcol) of a wider matrix [N, ldx].
+//   dY2 != null: dX (+)= dY . W[:, wcol : +64] + dY2 . W[:, wcol + 64 : +64]   (two K chunks, one launch)
+//   ngroups > 1: dX[:, xcol + 64 g : +64] = dY . W[:, wcol + 64 g : +64] for g < ngroups (one operand conversion)
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
-               int accumulate, int64_t N, cudaStream_t st) {
+               int accumulate, int64_t N, cudaStream_t st, const float* dY2 = nullptr, int ngroups = 1) {
     if (N == 0) return GCRL_OK;
-    CUtensorMap ty, tx;
+    CUtensorMap ty, ty2, tx;
     int rc;
     if ((rc = make_tmap_rows(&ty, dY, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&ty2, dY2 ? dY2 : dY, N, 64))) return rc;
     if ((rc = make_tmap_rows(&tx, dX, N, ldx))) return rc;
     RowsGemmArgs a;
     a.W0 = W; a.ldW0 = ldw; a.col0 = wcol; a.W1 = nullptr; a.ldW1 = 0; a.col1 = 0;
-    a.bias0 = nullptr; a.bias1 = nullptr; a.relu = 0; a.n1 = 1; a.n2 = 0;
+    a.bias0 = nullptr; a.bias1 = nullptr; a.relu = 0; a.n1 = 1; a.n2 = dY2 ? 1 : 0;
     a.xt = nullptr; a.Dt = 0; a.Wt = nullptr; a.ldWt = 0; a.colt = 0;
-    a.wT = 1; a.ocol0 = xcol; a.ocol1 = 0; a.mask = mask; a.ldmask = 64; a.accumulate = accumulate; a.N = N;
-    return x3 ? launch_rows_gemm<64, true>(ty, ty, tx, tx, a, st) : launch_rows_gemm<64, false>(ty, ty, tx, tx, a, st);
+    a.wT = 1; a.ngroups = ngroups; a.ocol0 = xcol; a.ocol1 = 0; a.mask = mask; a.ldmask = 64; a.accumulate = accumulate; a.N = N;
+    return x3 ? launch_rows_gemm<64, true>(ty, ty2, tx, tx, a, st) : launch_rows_gemm<64, false>(ty, ty2, tx, tx, a, st);
 }
 
 // G[o][gcol0 + k] += sum_r Y[r][o] X[r][k] for X = [X1 (64 n1 columns) | X2 (64 n2 columns)]
 int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
-               int gcol0, int64_t N, cudaStream_t st) {
+               int gcol0, float* gbias, int64_t N, cudaStream_t st) {
     if (N == 0) return GCRL_OK;
     CUtensorMap ty, t1, t2;
     int rc;
@@ -486,8 +533,8 @@ int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const 
     if ((rc = make_tmap_rows(&t1, X1, N, ld1))) return rc;
     if ((rc = make_tmap_rows(&t2, n2 ? X2 : X1, N, n2 ? ld2 : ld1))) return rc;
     RowsWgradArgs a;
-    a.n1 = n1; a.n2 = n2; a.G = G; a.ldG = ldG; a.gcol0 = gcol0; a.N = N;
-    const int smem = 2 * 32768 + 2 * 32768 + 64 + 1024;
+    a.n1 = n1; a.n2 = n2; a.G = G; a.ldG = ldG; a.gcol0 = gcol0; a.gbias = gbias; a.N = N;
+    const int smem = 2 * 32768 + 2 * 32768 + 64 + 256 + 1024;
     static bool done = false;
     if (!done) {
         GCRL_CUDA(cudaFuncSetAttribute(k_rows_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

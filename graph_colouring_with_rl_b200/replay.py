@@ -93,14 +93,20 @@ class DeviceReplayBuffer(object):
         if (gids < 0).any():
             raise IndexError('replay slot never written')
         ns = self.pool.ns[gids]
-        node_off = np.concatenate([[0], np.cumsum(ns)])
-        adj_off = np.concatenate([[0], np.cumsum(ns * ns)])
         dev = self.device
+        # node offsets, adjacency offsets, vertex names and the slots themselves: one host->device copy
+        node_off, adj_off, names, slots_d = TransitionBatch.index_to_device(ns, dev, extra=batch)
+        n_vert, n_adj = int(ns.sum()), int((ns * ns).sum())
         adj, cur, nxt, action, reward, done = ops.replay_gather(
-            torch.from_numpy(batch.astype(np.int32)).to(dev), self.ring, self.pool.adj, self.pool.adj_off,
-            self.pool.n, self.pool.n_max, torch.from_numpy(node_off.astype(np.int32)).to(dev),
-            torch.from_numpy(adj_off.astype(np.int64)).to(dev), int(node_off[-1]), int(adj_off[-1]), err=self._err)
-        return TransitionBatch(ns, adj, cur, nxt, action, reward, done)
+            slots_d.int(), self.ring, self.pool.adj, self.pool.adj_off, self.pool.n, self.pool.n_max, node_off,
+            self._adj_off_plus(adj_off, n_adj), n_vert, n_adj, err=self._err)
+        return TransitionBatch(ns, adj, cur, nxt, action, reward, done, index_dev=(node_off, adj_off, names))
+
+    @staticmethod
+    def _adj_off_plus(adj_off, n_adj):
+        """gcrl_replay_gather takes [batch + 1] adjacency offsets; the kernel reads entries [0, batch) only (the last one is
+        the total, which it gets as a size), so the [batch] view is passed with one padding element when it is empty."""
+        return adj_off if adj_off.numel() else adj_off.new_zeros(1)
 
     def sample_buffer(self, sample_size):
         return self.gather(self.sample_indices(sample_size))

@@ -16,9 +16,10 @@ FIELDS = ('adj', 'cur_colour', 'next_colour', 'action', 'reward', 'done')
 
 
 class TransitionBatch(object):
-    def __init__(self, ns, adj, cur_colour, next_colour, action, reward, done):
+    def __init__(self, ns, adj, cur_colour, next_colour, action, reward, done, index_dev=None):
         """ns: host int64 [G] vertex counts; the rest are device tensors
-        (adj uint8 [sum n^2], colours int32 [N], action int32 [G], reward f32 [G], done int32 [G])."""
+        (adj uint8 [sum n^2], colours int32 [N], action int32 [G], reward f32 [G], done int32 [G]).
+        index_dev: (node_off int32 [G+1], adj_off int64 [G], names f32 [N]) if the caller already has them on the device."""
         self.ns = np.asarray(ns, dtype=np.int64)
         self.adj, self.cur_colour, self.next_colour = adj, cur_colour, next_colour
         self.action, self.reward, self.done = action, reward, done
@@ -30,11 +31,32 @@ class TransitionBatch(object):
         self.edge_off_h = np.concatenate([[0], np.cumsum(self.ns * (self.ns - 1))]).astype(np.int64)
         self.n_vertices = int(self.node_off_h[-1])
         self.n_edges = int(self.edge_off_h[-1])
-        self.node_off = torch.from_numpy(self.node_off_h.astype(np.int32)).to(dev)
-        self.adj_off = torch.from_numpy(self.adj_off_h[:-1].copy()).to(dev)
-        counts = torch.from_numpy(self.ns).to(dev)
-        start = torch.repeat_interleave(self.node_off[:-1].long(), counts)
-        self.names = (torch.arange(self.n_vertices, device=dev) - start).float()   # x[:,0] (graph_colouring_env.py:124-128)
+        if index_dev is not None:
+            self.node_off, self.adj_off, self.names = index_dev
+        elif self.n_vertices <= (1 << 16):
+            # small batches: the index arrays travel in ONE host->device copy (a learn step at the reference's minibatch size
+            # is bound by host-side issue time: every separate pageable copy is a blocking call)
+            self.node_off, self.adj_off, self.names = self.index_to_device(self.ns, dev)[:3]
+        else:
+            self.node_off = torch.from_numpy(self.node_off_h.astype(np.int32)).to(dev)
+            self.adj_off = torch.from_numpy(self.adj_off_h[:-1].copy()).to(dev)
+            counts = torch.from_numpy(self.ns).to(dev)
+            start = torch.repeat_interleave(self.node_off[:-1].long(), counts, output_size=self.n_vertices)   # (no sync)
+            self.names = (torch.arange(self.n_vertices, device=dev) - start).float()   # x[:,0] (graph_colouring_env.py:124-128)
+
+    @staticmethod
+    def index_to_device(ns, dev, extra=None):
+        """[node_off | adj_off | vertex names | extra] as ONE int64 host->device copy -> (node_off int32 [G+1], adj_off int64
+        [G], names f32 [N], extra int64 or None)."""
+        ns = np.asarray(ns, dtype=np.int64)
+        G, N = int(ns.size), int(ns.sum())
+        node_off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int64)
+        adj_off = np.concatenate([[0], np.cumsum(ns * ns)[:-1]]).astype(np.int64) if G else np.zeros(0, dtype=np.int64)
+        names = np.arange(N, dtype=np.int64) - np.repeat(node_off[:-1], ns)
+        parts = [node_off, adj_off, names] + ([np.asarray(extra, dtype=np.int64)] if extra is not None else [])
+        d = torch.from_numpy(np.concatenate(parts)).to(dev, non_blocking=True)
+        return (d[:G + 1].int(), d[G + 1:2 * G + 1], d[2 * G + 1:2 * G + 1 + N].float(),
+                d[2 * G + 1 + N:] if extra is not None else None)
 
     @classmethod
     def empty(cls, device):
@@ -229,7 +251,7 @@ def synthetic_transitions(adjs, frac_coloured, seed, device):
     steps = int(frac_coloured * int(env.ns.max()))
     target = torch.from_numpy((frac_coloured * env.ns).astype(np.int64)).to(env.device)
     counts = torch.from_numpy(env.ns).to(env.device)
-    gid = torch.repeat_interleave(torch.arange(env.n_graphs, device=env.device), counts)
+    gid = torch.repeat_interleave(torch.arange(env.n_graphs, device=env.device), counts, output_size=env.n_vertices)
     for _ in range(steps):
         coloured = torch.zeros(env.n_graphs, dtype=torch.long, device=env.device).index_add_(0, gid, (env.colour >= 0).long())
         uncol = counts - coloured
