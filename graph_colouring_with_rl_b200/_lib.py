@@ -59,6 +59,7 @@ SIGNATURES = {
     'gcrl_soft_update': (c_int, [P, P, c_int64, c_float, P]),
     'gcrl_env_reset': (c_int, [P, P, P, P, c_int32, c_int64, P]),
     'gcrl_env_step': (c_int, [P, P, P, c_int32, P, P, P, P, P, P, P]),
+    'gcrl_env_step_greedy': (c_int, [P, P, P, c_int32, P, P, P, P, P, P, P, P]),
     'gcrl_env_first_vertex': (c_int, [P, P, P, c_int32, P, P, P]),
     'gcrl_replay_store': (c_int, [c_int32, P, P, P, P, P, P, P, P, c_int32, P, P, P, P, P, P, P]),
     'gcrl_replay_gather': (c_int, [c_int32, P, P, P, P, P, P, P, c_int32, P, P, P, c_int32, P, P, P, P, P, P,

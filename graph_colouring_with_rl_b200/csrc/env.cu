@@ -55,22 +55,57 @@ __global__ void __launch_bounds__(ENV_THREADS) k_env_step(
     const uint8_t* __restrict__ adj, const int64_t* __restrict__ adj_off,
     const int32_t* __restrict__ node_off, int32_t G, const int32_t* __restrict__ action,
     int32_t* __restrict__ colour, int32_t* __restrict__ max_colour, float* __restrict__ reward,
-    int32_t* __restrict__ done, float* __restrict__ x, int32_t* __restrict__ err) {
+    int32_t* __restrict__ done, float* __restrict__ x, int32_t* __restrict__ err,
+    const float* __restrict__ q, int32_t* __restrict__ action_out) {
     pdl_prologue();
     __shared__ int32_t col_s[ENV_MAX_N];
     __shared__ uint32_t used_s[ENV_WARPS][ENV_WORDS];
     __shared__ int32_t maxc_s, uncol_s;
+    __shared__ float bq_s[ENV_WARPS];
+    __shared__ int32_t ba_s[ENV_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int g = blockIdx.x; g < G; g += gridDim.x) {
         const int32_t v0 = node_off[g], n = node_off[g + 1] - v0;
         if (n > ENV_MAX_N) { if (tid == 0 && err) *err = 1; continue; }
         const uint8_t* A = adj + adj_off[g];
         const int words = (n + 31) >> 5;
-        const int32_t a = action[g];
         const int32_t prev_max = max_colour[g];
         for (int i = tid; i < n; i += ENV_THREADS) col_s[i] = colour[v0 + i];
         if (tid == 0) { maxc_s = prev_max; uncol_s = 0; }
         __syncthreads();
+        int32_t a;
+        if (q) {
+            // greedy action scoring fused into the step (dqn_agent.py:131-134): first maximum of q over the uncoloured
+            // vertices = np.argmax over the ascending unassigned list; -1 when the graph is finished
+            float best = -INFINITY;
+            int32_t arg = -1;
+            for (int i = tid; i < n; i += ENV_THREADS) {
+                if (col_s[i] < 0) {
+                    const float v = q[v0 + i];
+                    if (arg < 0 || v > best) { best = v; arg = i; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int32_t oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+            }
+            if (lane == 0) { bq_s[wid] = best; ba_s[wid] = arg; }
+            __syncthreads();
+            best = bq_s[0]; arg = ba_s[0];
+#pragma unroll
+            for (int w = 1; w < ENV_WARPS; ++w) {
+                const float ob = bq_s[w];
+                const int32_t oa = ba_s[w];
+                if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+            }
+            a = arg;
+            if (tid == 0 && action_out) action_out[g] = a;
+            __syncthreads();            // bq_s / ba_s are reused by the next graph of this CTA
+        } else {
+            a = action[g];
+        }
         const bool act = (a >= 0 && a < n && col_s[a] < 0);
         if (a >= n && tid == 0 && err) *err = 2;   // graph_colouring_env.py:72-73 raises
         if (act) {
@@ -223,7 +258,20 @@ int gcrl_env_step(const uint8_t* adj, const int64_t* adj_off, const int32_t* nod
     GCRL_CHECK_ARG(adj && adj_off && node_off && action && colour && max_colour);
     int blocks = G < sm_count() * 16 ? G : sm_count() * 16;
     launch_k(k_env_step, dim3(blocks), dim3(ENV_THREADS), 0, (cudaStream_t)stream, adj, adj_off, node_off, G, action, colour,
-                                                                max_colour, reward, done, x, nullptr);
+             max_colour, reward, done, x, nullptr, nullptr, nullptr);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
+int gcrl_env_step_greedy(const uint8_t* adj, const int64_t* adj_off, const int32_t* node_off, int32_t G,
+                         const float* q, int32_t* action_out, int32_t* colour, int32_t* max_colour, float* reward,
+                         int32_t* done, float* x, void* stream) {
+    GCRL_CHECK_ARG(G >= 0);
+    if (G == 0) return GCRL_OK;
+    GCRL_CHECK_ARG(adj && adj_off && node_off && q && colour && max_colour);
+    int blocks = G < sm_count() * 16 ? G : sm_count() * 16;
+    launch_k(k_env_step, dim3(blocks), dim3(ENV_THREADS), 0, (cudaStream_t)stream, adj, adj_off, node_off, G, nullptr, colour,
+             max_colour, reward, done, x, nullptr, q, action_out);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

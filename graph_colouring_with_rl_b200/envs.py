@@ -271,5 +271,10 @@ class BatchedColouringEnv(object):
         ops.env_step(self.adj, self.adj_off, self.node_off, actions, self.colour, self.max_colour, self.reward,
                      self.done, self.x)
 
+    def step_greedy(self, q):
+        """Argmax-Q over the uncoloured vertices of every graph fused with the step -> the actions taken, int32 [G]."""
+        return ops.env_step_greedy(self.adj, self.adj_off, self.node_off, q, self.colour, self.max_colour, self.reward,
+                                   self.done, self.x)
+
     def colours_used(self):
         return self.max_colour + 1

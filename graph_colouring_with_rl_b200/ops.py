@@ -281,6 +281,19 @@ def env_step(adj, adj_off, node_off, action, colour, max_colour, reward, done, x
                                 ptr(max_colour), ptr(reward), ptr(done), ptr(x), stream_ptr(dev)), 'gcrl_env_step')
 
 
+def env_step_greedy(adj, adj_off, node_off, q, colour, max_colour, reward, done, x, action_out=None):
+    """Masked per-graph first-argmax of q fused with the environment step; returns the actions taken (int32 [G])."""
+    lib = _lib.load()
+    dev = colour.device
+    G = int(node_off.numel()) - 1
+    if action_out is None:
+        action_out = _i32(G, dev)
+    with torch.cuda.device(dev):
+        check(lib.gcrl_env_step_greedy(ptr(adj), ptr(adj_off), ptr(node_off), G, ptr(q.contiguous()), ptr(action_out), ptr(colour),
+                                       ptr(max_colour), ptr(reward), ptr(done), ptr(x), stream_ptr(dev)), 'gcrl_env_step_greedy')
+    return action_out
+
+
 def env_first_vertex(adj, adj_off, node_off, n_vertices, want_counts=False):
     lib = _lib.load()
     dev = adj.device

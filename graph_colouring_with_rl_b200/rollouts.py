@@ -2,9 +2,10 @@
 neighbour-count rule, then argmax-Q over uncoloured vertices until every graph is done
 (test_policy_functions.py:36-73, batch of G graphs instead of one graph at a time).
 
-Per step: gcrl_gn_forward (Q of every vertex of every graph) -> gcrl_score_argmax (masked
-per-graph first-argmax) -> gcrl_env_step (first-fit colour, leaf pass, observation update).
-Finished graphs get action -1 from the argmax (no uncoloured vertex) and are left alone.
+Per step: gcrl_gn_forward (Q of every vertex of every graph; the vertex side of each block and the
+fc1/fc2/fc3 head are one fused launch) -> gcrl_env_step_greedy (masked per-graph first-argmax fused
+with the first-fit colouring, leaf pass and observation update).  Finished graphs get action -1
+from the argmax (no uncoloured vertex) and are left alone.
 
 Every step of an episode has the same shapes and the same buffers (only the colours change), so the
 step -- about 30 kernel launches -- is captured ONCE into a CUDA graph and replayed: the host issues
@@ -32,8 +33,7 @@ class _GraphedStep(object):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode, ws=self.ws)
-            self.action = ops.score_argmax(q, env.colour, env.node_off)
-            env.step(self.action)
+            self.action = env.step_greedy(q)
 
     def replay(self):
         self.graph.replay()
@@ -42,9 +42,7 @@ class _GraphedStep(object):
 
 def _eager_step(env, net, packed, eattr, flat):
     _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
-    a = ops.score_argmax(q, env.colour, env.node_off)
-    env.step(a)
-    return a
+    return env.step_greedy(q)
 
 
 @torch.no_grad()

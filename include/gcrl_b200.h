@@ -207,6 +207,14 @@ int gcrl_env_step(const uint8_t* adj, const int64_t* adj_off, const int32_t* nod
                   int32_t* max_colour, float* reward, int32_t* done, float* x, void* stream);
 /* first-vertex rule of the rollout harness (test_policy_functions.py:46-47; counts built at
  * utils.py:522-533,559-565): argmax_v deg*n^2 + #dist2*n + #dist3, first max. */
+/* greedy rollout step: action scoring fused into the environment step (test_policy_functions.py:56 +
+ * dqn_agent.py:131-134 + graph_colouring_env.py:64-90 in one launch).  Per graph the action is the first
+ * maximum of q [N] over its uncoloured vertices (-1 = none left: the graph is left alone), written to
+ * action_out[G] (may be NULL); then exactly gcrl_env_step. */
+int gcrl_env_step_greedy(const uint8_t* adj, const int64_t* adj_off, const int32_t* node_off,
+                         int32_t n_graphs, const float* q, int32_t* action_out, int32_t* colour,
+                         int32_t* max_colour, float* reward, int32_t* done, float* x, void* stream);
+
 int gcrl_env_first_vertex(const uint8_t* adj, const int64_t* adj_off, const int32_t* node_off,
                           int32_t n_graphs, int32_t* action, int32_t* dist_counts,
                           void* stream);

@@ -129,3 +129,25 @@ def test_rollouts_identical_eager_graphed_and_without_pdl():
         line = [l for l in out.stdout.splitlines() if l.startswith('RESULT')][0]
         want = 'RESULT %s %s' % (a['colours_used'].cpu().tolist(), torch.stack(a['actions']).cpu().tolist())
         assert line == want
+
+
+def test_env_step_greedy_equals_argmax_then_step():
+    """gcrl_env_step_greedy (masked first-argmax fused into the environment step) == gcrl_score_argmax followed by
+    gcrl_env_step, bit for bit: colours, colour counts, rewards, done flags, observations and the actions taken, with
+    exact Q ties (first maximum = lowest vertex index, dqn_agent.py:131-134) and finished graphs (action -1)."""
+    from graph_colouring_with_rl_b200 import ops
+    from graph_colouring_with_rl_b200.envs import BatchedColouringEnv
+    rng = np.random.default_rng(4)
+    adjs = [er(int(n), 0.35, rng) for n in rng.integers(1, 70, size=97)] + [er(300, 0.1, rng)]
+    e1 = BatchedColouringEnv(adjs, device=DEV)
+    e2 = BatchedColouringEnv(adjs, device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    for step in range(75):
+        q = torch.randint(0, 4, (e1.n_vertices,), generator=gen, device=DEV).float()       # many exact ties
+        a1 = ops.score_argmax(q, e1.colour, e1.node_off)
+        e1.step(a1)
+        a2 = e2.step_greedy(q)
+        assert torch.equal(a1, a2), step
+        for k in ('colour', 'max_colour', 'reward', 'done', 'x'):
+            assert torch.equal(getattr(e1, k), getattr(e2, k)), (step, k)
+    assert bool((a2[:97] == -1).all())          # the small graphs finished long ago
