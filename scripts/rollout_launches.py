@@ -20,7 +20,7 @@ flat = net.flat_params()
 env.step(env.first_vertices())
 def step():
     _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode)
-    env.step(ops.score_argmax(q, env.colour, env.node_off))
+    env.step_greedy(q)
 for _ in range(3):
     step()
 torch.cuda.synchronize()
