@@ -345,14 +345,21 @@ int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, co
     if (rc) return rc;
     rc = make_tmap_rows64(&tout, m_out ? m_out : Pi, m_out ? E : N, 128);
     if (rc) return rc;
-    // Work items are runs of whole segments of about item_edges edges, one warp group walks an item tile by tile.  Large
-    // batches: ITEM_EDGES (16 tiles).  Small ones (a 64-graph replay minibatch is 70 k edges = 34 such items for 592 warp
-    // groups: the launch took 0.22 ms, one group's serial time): shrink the items until every group has one.
+    // Work items are runs of whole segments of about item_edges edges; one warp group walks an item tile by tile, items are
+    // dealt round-robin.  Round 1 used 2 048-edge items whatever E: a rollout shard of 1 250 x 50-vertex graphs (3.06 M edges)
+    // is 2.5 such items per group, so a third of the groups walked 3 items and the rest 2 -- the 0.82 strong-scaling
+    // efficiency of the rollouts at N = 8.  Now every group gets the same number k of items:
+    //   * inference (no arg tracking): k = 1, ONE contiguous run of E / groups edges per group, like the backward's contiguous
+    //     tile ranges (measured on 10 000 x 50-vertex rollouts: 0.447 -> 0.469 of the HBM peak per launch);
+    //   * training (stash + arg tracking): the smallest k that keeps an item within ITEM_EDGES; contiguous runs measured
+    //     SLOWER here (3.46 -> 3.92 ms per 512 x 200-vertex launch), so the compact streaming window is kept.
+    // Small batches (a 64-graph replay minibatch is 70 k edges) end up with one tile per group either way.
     {
         const int64_t groups = (int64_t)sm_count() * WG_N;
-        int64_t ie = (E + groups - 1) / groups;
-        ie = (ie + TILE - 1) / TILE * TILE;
-        a.item_edges = (int)(ie < TILE ? TILE : (ie > ITEM_EDGES ? ITEM_EDGES : ie));
+        const int64_t k = amin != nullptr ? (E + groups * ITEM_EDGES - 1) / (groups * ITEM_EDGES) : 1;
+        int64_t ie = (E + groups * k - 1) / (groups * k);
+        if (k == 1) ie = (ie + TILE - 1) / TILE * TILE;
+        a.item_edges = (int)(ie < TILE ? TILE : ie);
     }
     const int64_t items = (E + a.item_edges - 1) / a.item_edges;
     int64_t grid = sm_count();
