@@ -288,3 +288,58 @@ def test_make_target_builds_the_keys_the_hot_path_reads():
     assert np.array_equal(t['neighbour_dist_counts'], g['dist_counts'].astype(np.float64))
     assert len(t['present_edges']) == int(g['adj'].sum())
     assert t['edge_ind_dict'][0][1] == 0 and t['edge_ind_dict'][1][0] == 1
+
+
+def test_learn_collates_next_states_separately_when_their_edges_differ():
+    """a caller whose next_data carries OTHER edge attributes / another edge order than data (the reference batches
+    next_datas on their own, dqn_agent.py:55-56,187) must get Q targets from those edges, not from a layout shared with the
+    current states.  Plain Data objects (no dense adjacency), next-state edges permuted and with attributes of a DIFFERENT
+    graph; loss against the oracle's learn step with separately collated batches; and the shortcut's own answer differs."""
+    from graph_colouring_with_rl_b200.data import Data
+    from graph_colouring_with_rl_b200.dqn_agent import DQNAgentGN
+    rng = np.random.default_rng(12)
+    params = util.load_parity_weights()
+    gids = [3, 17, 42, 58, 71, 90]
+    torch.manual_seed(0)
+    agent = DQNAgentGN(2, 1, 0)
+    agent.gn_behaviour.load_state_dict(params)
+    agent.soft_update(agent.gn_behaviour, agent.gn_target, 1)
+    cur_obs, nxt_obs, acts, rews, dones, assigned = [], [], [], [], [], []
+    for gi in gids:
+        g = GRAPHS[gi]
+        n = g['n']
+        col = util.random_colours(n, g['adj'], 0.4, rng)
+        un = np.nonzero(col < 0)[0]
+        a = int(rng.choice(un))
+        ncol = col.copy()
+        ncol[a] = 0
+        x, ei, ea = gn_oracle.observation(g['adj'], col, g['edge_list'])
+        # next state: same vertices, but the edge list is permuted and the attributes are those of the COMPLEMENT graph
+        perm = torch.from_numpy(rng.permutation(ei.shape[1]))
+        comp = (1 - g['adj']) * (1 - np.eye(n, dtype=g['adj'].dtype))
+        xn, ein, ean = gn_oracle.observation(comp, ncol, g['edge_list'])
+        ein, ean = ein[:, perm], ean[perm]
+        cur_obs.append((x, ei, ea))
+        nxt_obs.append((xn, ein, ean))
+        acts.append(a); rews.append(-1.0 if rng.random() < 0.3 else 0.0); dones.append(0)
+        assigned.append((ncol >= 0).astype(np.int64))
+        agent.remember(Data(x=x, edge_index=ei, edge_attr=ea), [], assigned[-1], a, rews[-1],
+                       Data(x=xn, edge_index=ein, edge_attr=ean), [], 0)
+    res = gn_oracle.learn_step(params, params, {}, gn_oracle.collate(cur_obs), gn_oracle.collate(nxt_obs),
+                               [GRAPHS[g]['n'] for g in gids], acts, rews, dones, np.concatenate(assigned))
+    loss = float(agent.learn_on(np.arange(len(gids))).item())
+    assert abs(loss - res['loss']) <= 1e-4 * max(1.0, abs(res['loss'])), (loss, res['loss'])
+    # what sharing the current layout for the next states would have given is a different number
+    shared = gn_oracle.learn_step(params, params, {}, gn_oracle.collate(cur_obs),
+                                  gn_oracle.collate([(xn, ei, ea) for (xn, _, _), (_, ei, ea) in zip(nxt_obs, cur_obs)]),
+                                  [GRAPHS[g]['n'] for g in gids], acts, rews, dones, np.concatenate(assigned))
+    assert abs(shared['loss'] - res['loss']) > 1e-3 * max(1.0, abs(res['loss']))
+    with pytest.raises(ValueError):
+        agent.choose_action(Data(x=x, edge_index=ei, edge_attr=ea), [], [], test_mode=True)
+
+
+def test_oversized_graphs_are_rejected_not_skipped():
+    from graph_colouring_with_rl_b200 import envs
+    with pytest.raises(ValueError, match='at most 4096'):
+        envs.check_graph_sizes([10, 5000])
+    envs.check_graph_sizes([1, 4096])
