@@ -124,6 +124,26 @@ def stream_ptr(device=None):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class _NoGuard(object):
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(dev):
+    """`torch.cuda.device(dev)` only when dev is not already the current device: the context manager costs ~10 us per
+    call, and a small learn step makes fifteen library calls (it is bound by host issue time)."""
+    idx = dev.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(dev)
+
+
 _ws_cache = {}
 
 

@@ -159,7 +159,7 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None, target_flat=None, tau=0.0, grad=None):
         loss = closure() if closure is not None else None
-        flat = self._net.flat_params()
+        flat = self._net.flat_params(full_check=grad is None)
         if grad is None:
             grad = self._flat_grad()
         if self.exp_avg is None or self.exp_avg.device != flat.device:
@@ -253,14 +253,19 @@ class GNNetwork(nn.Module):
             self.__dict__['_params_cached'] = pl
         return pl
 
-    def flat_params(self):
+    def flat_params(self, full_check=True):
         """The [198 529] fp32 buffer all parameters alias.  Rebuilt (and the parameters
-        re-pointed) if anything replaced a parameter's storage, e.g. `.to()` or `.data = ...`."""
+        re-pointed) if anything replaced a parameter's storage, e.g. `.to()` or `.data = ...`.
+        full_check=False (the learner's and the rollouts' inner loops, which own the network between calls) looks at the
+        first and the last parameter only: module-wide moves (`.to()`, `load_state_dict(assign=True)`) are still seen."""
         params = self._param_list()
         flat = self._flat
         if flat is not None:
             base = flat.data_ptr()
-            if all(p.data_ptr() == base + 4 * off for p, off in zip(params, self._offsets)):
+            if not full_check:
+                if params[0].data_ptr() == base and params[-1].data_ptr() == base + 4 * self._offsets[-1]:
+                    return flat
+            elif all(p.data_ptr() == base + 4 * off for p, off in zip(params, self._offsets)):
                 return flat
         assert [p.numel() for p in params] == [b - a for a, b in zip(self._offsets, self._offsets[1:] + [self._n_params])], \
             'parameter order does not match the library layout'

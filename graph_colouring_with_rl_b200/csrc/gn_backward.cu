@@ -520,7 +520,7 @@ static int launch_edge_bwd(const EdgeBwdArgs& a, bool first, cudaStream_t st) {
 // gn_backward_wg.cu: PNA backward coefficients and the two-group tensor-core edge backward
 int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
                         float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
-                        float* gb2_vertex, cudaStream_t st);
+                        float* gb2_vertex, float* zero_ptr, int64_t zero_n, cudaStream_t st);
 int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev, int De,
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
@@ -531,6 +531,14 @@ int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, floa
                int accumulate, int64_t N, cudaStream_t st, const float* dY2 = nullptr, int ngroups = 1);
 int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
                int gcol0, float* gbias, int64_t N, cudaStream_t st);
+int linear_bwd_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
+                  int gcol0, float* gbias, const float* W, int ldW, int wcol0, uint32_t dx_chunks, uint32_t mask_chunks,
+                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st);
+// GCRL_VBWD_IMPL=split: the vertex side of the backward as separate weight-gradient / data-gradient launches (A/B switch)
+static bool vbwd_fused() {
+    static const bool split = getenv("GCRL_VBWD_IMPL") && getenv("GCRL_VBWD_IMPL")[0] == 's';
+    return !split;
+}
 
 // first stage of the head's backward (architecture.py:197 fc3 and the ReLU in front of it) in one launch:
 //   dy2[r][k] = dq[r] F3[k] [y2[r][k] > 0],   gF3[k] += sum_r dq[r] y2[r][k],   gf3 += sum_r dq[r]
@@ -627,10 +635,18 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
             launch_k(k_head_bwd_first, dim3((int)blocks), dim3(256), 0, st, d_q, S.y2, hd.F3, N, dy2, G(hd.F3), G(hd.f3));
             GCRL_LAUNCH_CHECK();
+            if (vbwd_fused()) {
+                // one launch per Linear layer: weight gradient, bias gradient and (masked) data gradient together
+                RC(linear_bwd_tc(x3h, dy2, S.y1, 64, 1, nullptr, 0, 0, G(hd.F2), 64, 0, G(hd.f2), hd.F2, 64, 0, 1u, 1u,
+                                 dy1, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+                RC(linear_bwd_tc(x3h, dy1, h5, 64, 1, nullptr, 0, 0, G(hd.F1), 64, 0, G(hd.f1), hd.F1, 64, 0, 1u, 0u,
+                                 dh, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+            } else {
             RC(wgrad64_tc(x3h, dy2, S.y1, 64, 1, nullptr, 0, 0, G(hd.F2), 64, 0, G(hd.f2), N, st));
             RC(dgrad64_tc(x3h, dy2, hd.F2, 64, 0, dy1, 64, 0, S.y1, 0, N, st));
             RC(wgrad64_tc(x3h, dy1, h5, 64, 1, nullptr, 0, 0, G(hd.F1), 64, 0, G(hd.f1), N, st));
             RC(dgrad64_tc(x3h, dy1, hd.F1, 64, 0, dh, 64, 0, nullptr, 0, N, st));
+            }
         } else {
         RC(wgrad(d_q, 1, 1, S.y2, 64, 64, G(hd.F3), 64, 0, N, st));              // dF3
         RC(colsum(d_q, N, 1, G(hd.f3), st));                                     // df3
@@ -675,7 +691,17 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         static const bool node_ffma = getenv("GCRL_NODE_IMPL") && getenv("GCRL_NODE_IMPL")[0] == 'f';
         const bool vtc = math_mode != GCRL_MATH_FP32 && !node_ffma;
         const bool x3 = math_mode == GCRL_MATH_BF16X3;
-        if (vtc) {
+        if (vtc && vbwd_fused()) {
+            // update_mlp.2 and update_mlp.0, one launch each: weight + bias gradient, and the data gradient masked by the
+            // stashed relu output (du1) / written to d agg's four windows and dh_{l-1}
+            RC(linear_bwd_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, G(b.c2), b.U2, 64, 0, 1u, 1u,
+                             du1, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+            const int n2 = b.Dv == 64 ? 1 : 0;
+            const uint32_t dx = 0xFu | ((n2 && l > 0) ? 0x10u : 0u);
+            RC(linear_bwd_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, n2, G(b.U1), ldU1, 0, G(b.c1), b.U1, ldU1, 0, dx, 0u,
+                             dagg, 256, 0, 0, dh_prev, 64, 0, 0, N, st));
+            if (b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
+        } else if (vtc) {
             // bias gradients ride in the weight-gradient launches; d agg's four 64-column windows are one launch
             RC(wgrad64_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, G(b.c2), N, st));
             RC(dgrad64_tc(x3, dh, b.U2, 64, 0, du1, 64, 0, S.u1[l], 0, N, st));
@@ -694,7 +720,9 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         if (l > 0) RC(dgrad(du1, 64, 64, b.U1, ldU1, 256, 64, dh_prev, 64, nullptr, 0, N, st));
         }
         // message MLP + aggregation (architecture.py:51-66)
-        GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)(dPj - dPi) * 4 + (size_t)N * 64 * 4, st));     // dPi and dPj are adjacent
+        const int64_t dp_floats = (int64_t)(dPj - dPi) + N * 64;                                   // dPi and dPj are adjacent
+        const bool tc_edge = E > 0 && math_mode != GCRL_MATH_FP32 && ((l == 0) ? (b.De <= 8) : (b.De == 64));
+        if (!tc_edge) GCRL_CUDA(cudaMemsetAsync(dPi, 0, (size_t)dp_floats * 4, st));              // (else cleared by k_pna_bwd_coef)
         float* de_prev = (l > 0) ? deb[l & 1] : nullptr;
         const bool tc_ok = (l == 0) ? (b.De <= 8) : (b.De == 64);
         if (E > 0 && math_mode != GCRL_MATH_FP32 && tc_ok) {
@@ -703,7 +731,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             // them in its dm loop.  The forward stashed e_5, so block 5 runs as a regular block without the d e_l term.
             float* de_scatter = de_cur ? const_cast<float*>(de_cur) : nullptr;
             RC(launch_pna_bwd_coef(dagg, S.agg[l], S.var[l], seg_off, N, coef_a, coef_b, S.amin[l], S.amax[l], de_scatter,
-                                   nullptr, st));
+                                   nullptr, dPi, dp_floats, st));
             RC(launch_edge_bwd_wg(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E, S.e[l], de_cur, coef_a, coef_b,
                                   dagg, S.amin[l], S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
@@ -724,7 +752,15 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             RC(launch_edge_bwd(a, l == 0, st));
         }
         // vertex columns of message_mlp.0: Pi = A h + b1, Pj = B h
-        if (vtc && b.Dv == 64) {
+        const bool fused_w1 = vtc && b.Dv == 64 && vbwd_fused();
+        if (fused_w1) {
+            // Pi = A h + b1 and Pj = B h: gradient of the A / B columns of message_mlp.0 and dh_{l-1} += dPi A, += dPj B
+            const uint32_t dx = l > 0 ? 1u : 0u;
+            RC(linear_bwd_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), b.W1, ldW1, 0, dx, 0u,
+                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st));
+            RC(linear_bwd_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, b.W1, ldW1, 64, dx, 0u,
+                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st));
+        } else if (vtc && b.Dv == 64) {
             RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), N, st));
             RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, N, st));
         } else {
@@ -732,7 +768,9 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             RC(wgrad(dPj, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, b.Dv, N, st));
             RC(colsum(dPi, N, 64, G(b.b1), st));
         }
-        if (l > 0 && vtc) {
+        if (l > 0 && fused_w1) {
+            float* t = dh; dh = dh_prev; dh_prev = t;
+        } else if (l > 0 && vtc) {
             // dh_{l-1} += dPi A + dPj B: two K chunks of one launch
             RC(dgrad64_tc(x3, dPi, b.W1, ldW1, 0, dh_prev, 64, 0, nullptr, 1, N, st, dPj));
             float* t = dh; dh = dh_prev; dh_prev = t;

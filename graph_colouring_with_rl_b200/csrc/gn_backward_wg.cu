@@ -53,8 +53,12 @@ __global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __re
                                const float* __restrict__ var, const int32_t* __restrict__ seg_off, int64_t N,
                                float* __restrict__ ca, float* __restrict__ cb, const int32_t* __restrict__ amin,
                                const int32_t* __restrict__ amax, float* __restrict__ de_scatter,
-                               float* __restrict__ gb2_vertex) {
+                               float* __restrict__ gb2_vertex, float4* __restrict__ zero_ptr, int64_t zero_n4) {
     pdl_prologue();
+    // dPi | dPj of the edge kernel that follows start from zero: cleared here instead of by a memset node (which would
+    // also break the programmatic launch chain around it)
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < zero_n4; t += (int64_t)gridDim.x * blockDim.x)
+        zero_ptr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     // gb2_vertex != null (block 5, pipelined kernel): db2 = sum over edges of dm = sum_v (g_mean + g_min + g_max)
     // (the std term sums to zero over a segment), accumulated here instead of in the edge kernel
     float bacc = 0.f;
@@ -90,12 +94,13 @@ __global__ void k_pna_bwd_coef(const float* __restrict__ dagg, const float* __re
 
 int launch_pna_bwd_coef(const float* dagg, const float* agg, const float* var, const int32_t* seg_off, int64_t N,
                         float* ca, float* cb, const int32_t* amin, const int32_t* amax, float* de_scatter,
-                        float* gb2_vertex, cudaStream_t st) {
+                        float* gb2_vertex, float* zero_ptr, int64_t zero_n, cudaStream_t st) {
     if (N == 0) return GCRL_OK;
     int64_t blocks = (N * 64 + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    launch_k(k_pna_bwd_coef, dim3((int)blocks), dim3(256), 0, st, dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex);
+    launch_k(k_pna_bwd_coef, dim3((int)blocks), dim3(256), 0, st, dagg, agg, var, seg_off, N, ca, cb, amin, amax, de_scatter, gb2_vertex,
+             reinterpret_cast<float4*>(zero_ptr), zero_n / 4);
     GCRL_LAUNCH_CHECK();
     return GCRL_OK;
 }

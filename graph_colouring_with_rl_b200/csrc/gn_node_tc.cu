@@ -406,6 +406,257 @@ __global__ void __launch_bounds__(256, 1) k_rows_wgrad_tc(const __grid_constant_
     if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// ---- backward of one Linear layer in ONE launch (round 2) ---------------------------------------------------------------------
+// For Y = dL/d(out) [N,64], the layer's input X = [X1 (64 n1 columns) | X2 (64 n2 columns)] and its weights W [64, ld]:
+//   G[o][gcol0 + 64 c + k] += sum_r Y[r][o] X_c[r][k]        (weight gradient, one TMEM accumulator per chunk, flushed once)
+//   gbias[o]               += sum_r Y[r][o]                   (bias gradient)
+//   dX_c[r][k]             (+)= sum_o Y[r][o] W[o][wcol0 + 64 c + k]  [* (X_c[r][k] > 0)]     for the chunks in dx_chunks
+// k_rows_wgrad_tc computes the first two; the third used to be separate k_rows_gemm_tc launches that converted the same Y
+// tile again.  Here the Y operand tile (one byte layout for the row-contracting and the feature-contracting product) is
+// converted once per 128-vertex tile; per chunk the weight-gradient product and the data-gradient product are issued
+// together, and the data gradient's epilogue runs under the NEXT chunk's landing and conversion: it masks with the fp32
+// landing tile of X_c itself (relu' of the stashed activation, when the layer's input is that activation) and overwrites
+// that tile in place, which then leaves through a TMA store / reduce.  A 64-transition learn step's backward goes from 61
+// launches to ~41 (profiles/r02_launches_learn_step_64x15-50.json).
+struct LinearBwdArgs {
+    int n1, n2;
+    float* G; int ldG, gcol0;
+    float* gbias;
+    const float* W; int ldW, wcol0;
+    uint32_t dx_chunks, mask_chunks;       // bit c: chunk c produces dX / is masked by X_c > 0
+    int acc1, acc2;                        // outputs of map o1 (chunks < n1) / o2 (chunks >= n1) are added to memory
+    int ocol1, ocol2;                      // column of chunk 0 / chunk n1 inside their output matrices
+    int64_t N;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(256, 1) k_linear_bwd_tc(const __grid_constant__ CUtensorMap tmY,
+                                                         const __grid_constant__ CUtensorMap tm1,
+                                                         const __grid_constant__ CUtensorMap tm2,
+                                                         const __grid_constant__ CUtensorMap to1,
+                                                         const __grid_constant__ CUtensorMap to2, const LinearBwdArgs a) {
+    pdl_prologue();
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int nch = a.n1 + a.n2;
+    unsigned char* Wsm = base;                                          // [nch] weight tiles (hi 8 KB | lo 8 KB), dX chunks only
+    float* L0 = reinterpret_cast<float*>(base + nch * 16384);
+    float* L1 = L0 + 128 * 64;
+    unsigned char* Yop = reinterpret_cast<unsigned char*>(L1 + 128 * 64);
+    unsigned char* Xop = Yop + 32768;
+    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(Xop + 32768);      // [2]
+    uint64_t* bar_mma = bar_tma + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 3);
+    float* bsum_s = reinterpret_cast<float*>(bar_tma + 4);             // [64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sp = warp & 3, half = warp >> 2;
+    const int row = 32 * sp + lane;
+    if (tid < 64) bsum_s[tid] = 0.f;
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        mbar_init(&bar_tma[0], 1);
+        mbar_init(&bar_tma[1], 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    for (int c = 0; c < nch; ++c)
+        if ((a.dx_chunks >> c) & 1u)
+            load_weight_tile(a.W, a.ldW, a.wcol0 + 64 * c, reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384),
+                             reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384 + 8192), tid, 256);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_accd = tmem + 64 * NODE_MAX_CHUNKS;               // the data gradient's accumulator (after the <= 5 wgrad ones)
+    const uint32_t lane_addr = (uint32_t)(32 * sp) << 16;
+    const uint32_t id_rows = make_idesc_bf16(64, 64, true, true);
+    const uint32_t id_featT = make_idesc_bf16(128, 64, false, true);
+    uint32_t ph_tma[2] = {0u, 0u}, ph_mma = 0u;
+    auto issue_load = [&](int j, int32_t v0) {          // load j of a tile: 0 = Y, 1 + c = X chunk c; lands in buffer j & 1
+        float* L = (j & 1) ? L1 : L0;
+        const int c = j - 1;
+        const CUtensorMap* tm = j == 0 ? &tmY : (c < a.n1 ? &tm1 : &tm2);
+        const int col = j == 0 ? 0 : 64 * (c < a.n1 ? c : c - a.n1);
+        mbar_arrive_expect_tx(&bar_tma[j & 1], 128 * 64 * 4);
+        tma_load_2d(L, tm, col, v0, &bar_tma[j & 1]);
+        tma_load_2d(L + 128 * 32, tm, col + 32, v0, &bar_tma[j & 1]);
+    };
+    // data gradient of chunk c: accumulator -> (mask with X_c) -> in place over X_c's landing tile (buffer (c + 1) & 1)
+    auto dx_epilogue = [&](int c) {
+        float* L = ((c + 1) & 1) ? L1 : L0;
+        float acc[32];
+        tmem_ld32(t_accd + lane_addr + 32 * half, acc);
+        const bool masked = (a.mask_chunks >> c) & 1u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float4* p = reinterpret_cast<float4*>(l_ptr(L, row, 8 * half + k));
+            float4 r = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            if (masked) {
+                const float4 m = *p;
+                r.x = m.x > 0.f ? r.x : 0.f; r.y = m.y > 0.f ? r.y : 0.f;
+                r.z = m.z > 0.f ? r.z : 0.f; r.w = m.w > 0.f ? r.w : 0.f;
+            }
+            *p = r;
+        }
+    };
+    auto dx_store = [&](int c, int32_t v0) {             // thread 0 only (bulk groups are per thread)
+        const float* L = ((c + 1) & 1) ? L1 : L0;
+        const bool second = c >= a.n1;
+        const CUtensorMap* to = second ? &to2 : &to1;
+        const int col = second ? a.ocol2 + 64 * (c - a.n1) : a.ocol1 + 64 * c;
+        if (second ? a.acc2 : a.acc1) {
+            tma_reduce_add_2d(to, col, v0, L);
+            tma_reduce_add_2d(to, col + 32, v0, L + 128 * 32);
+        } else {
+            tma_store_2d(to, col, v0, L);
+            tma_store_2d(to, col + 32, v0, L + 128 * 32);
+        }
+        bulk_commit();
+        bulk_wait_read0();
+    };
+    const int64_t n_tiles = (a.N + 127) / 128;
+    bool first_tile = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int32_t v0 = (int32_t)(tile * 128);
+        if (tid == 0) { issue_load(0, v0); issue_load(1, v0); }
+        // ---- Y: bias gradient, operand tile ----------------------------------------------------------------------------------
+        mbar_wait_bounded(&bar_tma[0], ph_tma[0]);
+        ph_tma[0] ^= 1u;
+        if (a.gbias) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int t = it * 256 + tid;
+                const float4 v = *reinterpret_cast<const float4*>(l_ptr(L0, t >> 4, t & 15));
+                bacc.x += v.x; bacc.y += v.y; bacc.z += v.z; bacc.w += v.w;
+            }
+        }
+        convert_tile128<X3>(L0, reinterpret_cast<__nv_bfloat16*>(Yop), reinterpret_cast<__nv_bfloat16*>(Yop + 16384), tid);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0 && nch >= 2) issue_load(2, v0);                    // X chunk 1 -> the buffer Y has left
+        // ---- X chunks --------------------------------------------------------------------------------------------------------
+        for (int c = 0; c < nch; ++c) {
+            const int j = c + 1;
+            const float* L = (j & 1) ? L1 : L0;
+            mbar_wait_bounded(&bar_tma[j & 1], ph_tma[j & 1]);
+            ph_tma[j & 1] ^= 1u;
+            const bool prev_dx = c > 0 && ((a.dx_chunks >> (c - 1)) & 1u);
+            if (c > 0) {                                                // chunk c - 1's products have read Xop / written acc_d
+                mbar_wait_bounded(bar_mma, ph_mma);
+                ph_mma ^= 1u;
+                tc_fence_after();
+            }
+            convert_tile128<X3>(L, reinterpret_cast<__nv_bfloat16*>(Xop), reinterpret_cast<__nv_bfloat16*>(Xop + 16384), tid);
+            if (prev_dx) dx_epilogue(c - 1);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0 && c > 0) {
+                if (prev_dx) dx_store(c - 1, v0);                       // (waits until the store has read the tile)
+                if (c + 2 <= nch) issue_load(c + 2, v0);                // X chunk c + 1 -> the buffer chunk c - 1 has left
+            }
+            if (warp == 0 && elect_one()) {
+                tc_fence_after();
+                issue_gemm_rows<X3>(tmem + 64 * c, smem_u32(Yop), smem_u32(Yop) + 16384, smem_u32(Xop), smem_u32(Xop) + 16384,
+                                    id_rows, 128, !first_tile);
+                if ((a.dx_chunks >> c) & 1u) {
+                    const uint32_t w = smem_u32(Wsm + c * 16384);
+                    issue_gemm_featT<X3>(t_accd, smem_u32(Yop), smem_u32(Yop) + 16384, w, w + 8192, id_featT, false);
+                }
+                umma_commit(bar_mma);
+            }
+        }
+        mbar_wait_bounded(bar_mma, ph_mma);                             // the last chunk's products
+        ph_mma ^= 1u;
+        tc_fence_after();
+        if ((a.dx_chunks >> (nch - 1)) & 1u) {
+            dx_epilogue(nch - 1);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) dx_store(nch - 1, v0);
+        }
+        tc_fence_before();
+        __syncthreads();                                                // tiles, operands and acc_d are free for the next vertex tile
+        tc_fence_after();
+        first_tile = false;
+    }
+    if (tid == 0) bulk_wait0();
+    if (!first_tile) {
+        tc_fence_after();
+        if (warp < 4) {
+            const int o = 16 * warp + lane;               // accumulator row of an M = 64 product
+            const uint32_t la = (uint32_t)(32 * warp) << 16;
+            // 16-byte vector reds when every row of the gradient window is 16-byte aligned (not block 1's 258-wide U1)
+            const bool vec_flush = (((a.ldG | a.gcol0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
+            for (int c = 0; c < nch; ++c) {
+#pragma unroll 1
+                for (int hh = 0; hh < 2; ++hh) {
+                    float v[32];
+                    tmem_ld32(tmem + 64 * c + la + 32 * hh, v);
+                    float* gp = &a.G[o * a.ldG + a.gcol0 + 64 * c + 32 * hh];
+                    if (lane < 16) {
+                        if (vec_flush) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; jj += 4)
+                                atomicAdd(reinterpret_cast<float4*>(gp + jj), make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]));
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) atomicAdd(gp + jj, v[jj]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (a.gbias) {
+        const int c4 = tid & 15;
+        atomicAdd(&bsum_s[4 * c4 + 0], bacc.x); atomicAdd(&bsum_s[4 * c4 + 1], bacc.y);
+        atomicAdd(&bsum_s[4 * c4 + 2], bacc.z); atomicAdd(&bsum_s[4 * c4 + 3], bacc.w);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (a.gbias && !first_tile && tid < 64) atomicAdd(&a.gbias[tid], bsum_s[tid]);
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// Backward of one Linear layer (see k_linear_bwd_tc).  X1 [N, ld1] contributes n1 64-column chunks, X2 [N, ld2] n2; the data
+// gradients of chunks < n1 go to dX1 [N, ldo1] at column ocol1 + 64 c, those of the X2 chunks to dX2 [N, ldo2] at ocol2.
+int linear_bwd_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
+                  int gcol0, float* gbias, const float* W, int ldW, int wcol0, uint32_t dx_chunks, uint32_t mask_chunks,
+                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st) {
+    if (N == 0) return GCRL_OK;
+    const int nch = n1 + n2;
+    GCRL_CHECK_ARG(nch >= 1 && nch <= NODE_MAX_CHUNKS);
+    CUtensorMap ty, t1, t2, o1, o2;
+    int rc;
+    if ((rc = make_tmap_rows(&ty, Y, N, 64))) return rc;
+    if ((rc = make_tmap_rows(&t1, X1, N, ld1))) return rc;
+    if ((rc = make_tmap_rows(&t2, n2 ? X2 : X1, N, n2 ? ld2 : ld1))) return rc;
+    if ((rc = make_tmap_rows(&o1, dX1 ? dX1 : Y, N, dX1 ? ldo1 : 64))) return rc;
+    if ((rc = make_tmap_rows(&o2, dX2 ? dX2 : Y, N, dX2 ? ldo2 : 64))) return rc;
+    LinearBwdArgs a;
+    a.n1 = n1; a.n2 = n2; a.G = G; a.ldG = ldG; a.gcol0 = gcol0; a.gbias = gbias;
+    a.W = W; a.ldW = ldW; a.wcol0 = wcol0; a.dx_chunks = dx_chunks; a.mask_chunks = mask_chunks;
+    a.acc1 = acc1; a.acc2 = acc2; a.ocol1 = ocol1; a.ocol2 = ocol2; a.N = N;
+    const int smem = nch * 16384 + 2 * 32768 + 2 * 32768 + 64 + 256 + 1024;
+    static int max_set[2] = {0, 0};
+    if (smem > max_set[x3 ? 1 : 0]) {
+        if (x3) GCRL_CUDA(cudaFuncSetAttribute(k_linear_bwd_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else GCRL_CUDA(cudaFuncSetAttribute(k_linear_bwd_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set[x3 ? 1 : 0] = smem;
+    }
+    int64_t tiles = (N + 127) / 128;
+    int64_t grid = sm_count();
+    if (grid > tiles) grid = tiles;
+    if (x3) launch_k(k_linear_bwd_tc<true>, dim3((int)grid), dim3(256), smem, st, ty, t1, t2, o1, o2, a);
+    else launch_k(k_linear_bwd_tc<false>, dim3((int)grid), dim3(256), smem, st, ty, t1, t2, o1, o2, a);
+    GCRL_LAUNCH_CHECK();
+    return GCRL_OK;
+}
+
 // agg rows of vertices without incoming edges take the scatter defaults (0, 0, 0, sqrt(eps)): the edge kernel never
 // visits them (principal_neighbourhood_aggregation.py:45-64 on an empty segment)
 __global__ void k_fix_empty_agg(float* __restrict__ agg, const int32_t* __restrict__ seg_off, int64_t N) {

@@ -6,7 +6,7 @@ from collections import namedtuple
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr, workspace, require_cuda
+from ._lib import check, device_guard, ptr, stream_ptr, workspace, require_cuda
 
 HID = 64
 N_BLOCKS = 5
@@ -44,7 +44,7 @@ def pack(edge_index, n_vertices, validate=False):
     err = torch.zeros(1, dtype=torch.int32, device=dev) if validate else None
     nb = lib.gcrl_pack_workspace_bytes(N, E)
     ws = workspace(nb, dev, 'pack')
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_pack(ptr(ei), E, N, ptr(seg_off), ptr(src), ptr(dst), ptr(perm), ptr(err), ptr(ws),
                             ws.numel(), stream_ptr(dev)), 'gcrl_pack')
     if validate and int(err.item()) != 0:
@@ -62,7 +62,7 @@ def pack_dense(adj, adj_off, node_off, n_vertices, n_edges):
     seg_off, src, dst, perm = _i32(N + 1, dev), _i32(E, dev), _i32(E, dev), _i32(E, dev)
     eattr = torch.empty(E, 1, dtype=torch.float32, device=dev)
     ws = workspace(lib.gcrl_pack_dense_workspace_bytes(G), dev, 'pack')
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_pack_dense(ptr(adj), ptr(adj_off), ptr(node_off), G, N, E, ptr(seg_off), ptr(src),
                                   ptr(dst), ptr(perm), ptr(eattr), ptr(ws), ws.numel(), stream_ptr(dev)),
               'gcrl_pack_dense')
@@ -77,7 +77,7 @@ def permute_rows(t, perm, to_internal):
     rows = int(t.shape[0])
     width = int(t.numel() // max(rows, 1)) if rows else 1
     out = torch.empty_like(t)
-    with torch.cuda.device(t.device):
+    with device_guard(t.device):
         check(lib.gcrl_permute_rows(ptr(t), ptr(out), ptr(perm), rows, max(width, 1), 1 if to_internal else 0,
                                     stream_ptr(t.device)), 'gcrl_permute_rows')
     return out
@@ -98,7 +98,7 @@ def pna_forward(msg, seg_off, n_vertices, want_backward_state=False):
         amin = torch.empty(N, F, dtype=torch.int32, device=dev)
         amax = torch.empty(N, F, dtype=torch.int32, device=dev)
         var = torch.empty(N, F, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_pna_forward(ptr(msg), ptr(seg_off), N, E, F, ptr(out), ptr(amin), ptr(amax), ptr(var),
                                    stream_ptr(dev)), 'gcrl_pna_forward')
     if want_backward_state:
@@ -114,7 +114,7 @@ def pna_backward(msg, out, var, d_out, seg_off, dst, amin, amax):
     E, F = int(msg.shape[0]), int(msg.shape[1])
     N = int(out.shape[0])
     d_msg = torch.empty_like(msg)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_pna_backward(ptr(msg), ptr(out), ptr(var), ptr(d_out), ptr(seg_off), ptr(dst), ptr(amin),
                                     ptr(amax), N, E, F, ptr(d_msg), stream_ptr(dev)), 'gcrl_pna_backward')
     return d_msg
@@ -130,7 +130,7 @@ def segment_reduce(msg, seg_off, n_vertices, which):
     dev = msg.device
     E, F = int(msg.shape[0]), int(msg.shape[1])
     out = torch.empty(int(n_vertices), F, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_segment_reduce(ptr(msg), ptr(seg_off), int(n_vertices), E, F, SEGMENT_OPS[which],
                                       ptr(out), stream_ptr(dev)), 'gcrl_segment_reduce')
     return out
@@ -158,7 +158,7 @@ def gn_forward(params, dims, packed, x, eattr, gfeat=None, vgraph=None, with_sta
     nb_ws = lib.gcrl_gn_forward_workspace_bytes(N, E, 1 if with_stash else 0)
     if ws is None or ws.numel() < nb_ws:            # ws: a caller-owned workspace (CUDA-graph capture keeps its own)
         ws = workspace(nb_ws, dev, 'gn')
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_gn_forward(ptr(params), dims[0], dims[1], dims[2], N, E, ptr(packed.seg_off),
                                   ptr(packed.src), ptr(packed.dst), ptr(x), ptr(eattr), ptr(gfeat), ptr(vgraph),
                                   ptr(stash), ptr(h), ptr(q), ptr(ws), ws.numel(), math_mode, stream_ptr(dev)),
@@ -177,7 +177,7 @@ def gn_block_forward(params, dims, block, packed, x, eattr, math_mode=_lib.GCRL_
     upd = torch.empty(N, HID, dtype=torch.float32, device=dev)
     nb = 4 * N * (2 * 64 + 256 + 1) + 2048
     ws = workspace(nb, dev, 'gnblk')
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_gn_block_forward(ptr(params), dims[0], dims[1], dims[2], block, N, E, ptr(packed.seg_off),
                                         ptr(packed.src), ptr(packed.dst), ptr(x), ptr(eattr), ptr(msg), ptr(upd),
                                         ptr(ws), ws.numel(), math_mode, stream_ptr(dev)), 'gcrl_gn_block_forward')
@@ -198,7 +198,7 @@ def gn_backward(params, dims, packed, x, eattr, stash, d_q=None, d_h=None, gfeat
         ws = workspace(nb_ws, dev, 'gnbwd')
     d_q = d_q.contiguous() if d_q is not None else None
     d_h = d_h.contiguous() if d_h is not None else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_gn_backward(ptr(params), dims[0], dims[1], dims[2], N, E, ptr(packed.seg_off),
                                    ptr(packed.src), ptr(packed.dst), ptr(x.contiguous()), ptr(eattr.contiguous()),
                                    ptr(gfeat), ptr(vgraph), ptr(stash), ptr(d_q), ptr(d_h), ptr(grad),
@@ -216,7 +216,7 @@ def score_argmax(q, colour, node_off, want_q=False):
     G = int(node_off.numel()) - 1
     action = _i32(G, dev)
     qb = torch.empty(G, dtype=torch.float32, device=dev) if want_q else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_score_argmax(ptr(q.contiguous()), ptr(colour), ptr(node_off), G, ptr(action), ptr(qb),
                                     stream_ptr(dev)), 'gcrl_score_argmax')
     return (action, qb) if want_q else action
@@ -236,7 +236,7 @@ def td_target_loss(q_cur, q_next, next_colour, node_off, action, reward, done, g
     q_tgt = torch.empty(G, dtype=torch.float32, device=dev)
     d_q = torch.empty_like(q_cur)
     loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_td_target_loss(ptr(q_cur.contiguous()), ptr(q_next.contiguous()), ptr(next_colour),
                                       ptr(node_off), G, ptr(action), ptr(reward), ptr(done), float(gamma),
                                       int(batch_total), ptr(q_exp), ptr(q_tgt), ptr(d_q), ptr(loss), ptr(err),
@@ -248,7 +248,7 @@ def adam_soft_update(params, grad, exp_avg, exp_avg_sq, target, step, lr=1e-3, b
                      tau=1e-3):
     lib = _lib.load()
     dev = params.device
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_adam_soft_update(ptr(params), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(target),
                                         params.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
                                         int(step), float(tau), stream_ptr(dev)), 'gcrl_adam_soft_update')
@@ -257,7 +257,7 @@ def adam_soft_update(params, grad, exp_avg, exp_avg_sq, target, step, lr=1e-3, b
 def soft_update(behaviour, target, tau):
     lib = _lib.load()
     dev = behaviour.device
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_soft_update(ptr(behaviour), ptr(target), behaviour.numel(), float(tau), stream_ptr(dev)),
               'gcrl_soft_update')
 
@@ -267,7 +267,7 @@ def env_reset(colour, max_colour, x, node_off):
     lib = _lib.load()
     dev = colour.device
     G = int(node_off.numel()) - 1
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_env_reset(ptr(colour), ptr(max_colour), ptr(x), ptr(node_off), G, colour.numel(),
                                  stream_ptr(dev)), 'gcrl_env_reset')
 
@@ -276,7 +276,7 @@ def env_step(adj, adj_off, node_off, action, colour, max_colour, reward, done, x
     lib = _lib.load()
     dev = colour.device
     G = int(node_off.numel()) - 1
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_env_step(ptr(adj), ptr(adj_off), ptr(node_off), G, ptr(action), ptr(colour),
                                 ptr(max_colour), ptr(reward), ptr(done), ptr(x), stream_ptr(dev)), 'gcrl_env_step')
 
@@ -288,7 +288,7 @@ def env_step_greedy(adj, adj_off, node_off, q, colour, max_colour, reward, done,
     G = int(node_off.numel()) - 1
     if action_out is None:
         action_out = _i32(G, dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_env_step_greedy(ptr(adj), ptr(adj_off), ptr(node_off), G, ptr(q.contiguous()), ptr(action_out), ptr(colour),
                                        ptr(max_colour), ptr(reward), ptr(done), ptr(x), stream_ptr(dev)), 'gcrl_env_step_greedy')
     return action_out
@@ -300,7 +300,7 @@ def env_first_vertex(adj, adj_off, node_off, n_vertices, want_counts=False):
     G = int(node_off.numel()) - 1
     action = _i32(G, dev)
     counts = torch.empty(int(n_vertices), 3, dtype=torch.int32, device=dev) if want_counts else None
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_env_first_vertex(ptr(adj), ptr(adj_off), ptr(node_off), G, ptr(action), ptr(counts),
                                         stream_ptr(dev)), 'gcrl_env_first_vertex')
     return (action, counts) if want_counts else action
@@ -313,7 +313,7 @@ def replay_store(slot, graph_id, node_off, cur_colour, next_colour, action, rewa
     require_cuda(cur_colour, 'cur_colour')
     dev = cur_colour.device
     r_graph, r_cur, r_next, r_action, r_reward, r_done = ring
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_replay_store(int(slot.numel()), ptr(slot), ptr(graph_id), ptr(node_off), ptr(cur_colour),
                                     ptr(next_colour), ptr(action), ptr(reward), ptr(done), int(r_cur.shape[1]),
                                     ptr(r_graph), ptr(r_cur), ptr(r_next), ptr(r_action), ptr(r_reward), ptr(r_done),
@@ -332,7 +332,7 @@ def replay_gather(slots, ring, pool_adj, pool_adj_off, pool_n, n_max, out_node_o
     cur, nxt = _i32(n_vertices, dev), _i32(n_vertices, dev)
     action, done = _i32(B, dev), _i32(B, dev)
     reward = torch.empty(B, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with device_guard(dev):
         check(lib.gcrl_replay_gather(B, ptr(slots), ptr(r_graph), ptr(r_cur), ptr(r_next), ptr(r_action),
                                      ptr(r_reward), ptr(r_done), int(r_cur.shape[1]), ptr(pool_adj),
                                      ptr(pool_adj_off), ptr(pool_n), int(n_max), ptr(out_node_off),

@@ -10,7 +10,7 @@ with a single asynchronous NCCL all-reduce (794 KB) that the fused Adam's stream
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 FIELDS = ('adj', 'cur_colour', 'next_colour', 'action', 'reward', 'done')
 
@@ -139,6 +139,8 @@ class QLearner(object):
                                (torch.distributed.is_available() and torch.distributed.is_initialized())):
             self.world = torch.distributed.get_world_size(process_group)
         self._stash = None
+        self._side = None                # side stream + private forward workspace of the target forward (small minibatches)
+        self._side_ws = None
         self._gbuf = None
         self.keep_q = False              # tests: keep (q_expected, q_target) of the last fwd_bwd
         self.last_q = None
@@ -159,7 +161,7 @@ class QLearner(object):
         """[P + 2] floats: the behaviour net's flat gradient, then the loss and this rank's graph count -- one buffer,
         one all-reduce.  The net's `_flat_grad` (what FusedAdam reads) is the leading view."""
         net = self.agent.gn_behaviour
-        flat = net.flat_params()
+        flat = net.flat_params(full_check=False)
         P = flat.numel()
         g = self._gbuf
         if g is None or g.device != flat.device or g.numel() != P + 2 or net._flat_grad is None \
@@ -169,27 +171,28 @@ class QLearner(object):
         return g, P
 
     @torch.no_grad()
-    def target_q(self, batch):
-        """Target-network Q of every vertex of the next states (dqn_agent.py:187-188) -> [N]."""
+    def target_q(self, batch, slices=None, ws=None):
+        """Target-network Q of every vertex of the next states (dqn_agent.py:187-188) -> [N].
+        slices: micro-batch layouts already built for this batch (learn_step shares them between its two forwards)."""
         net = self.agent.gn_target
-        flat = net.flat_params()
+        flat = net.flat_params(full_check=False)
         out = torch.empty(batch.n_vertices, dtype=torch.float32, device=batch.device)
-        for g0, g1 in batch.micro_ranges(self.max_edges):
-            s = _Slice(batch, g0, g1)
+        for i, (g0, g1) in enumerate(batch.micro_ranges(self.max_edges)):
+            s = slices[i] if slices is not None else _Slice(batch, g0, g1)
             x = batch.x_of(batch.next_colour[s.v0:s.v1], s.v0, s.v1)
-            _, q, _ = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, math_mode=net.math_mode)
+            _, q, _ = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, math_mode=net.math_mode, ws=ws)
             out[s.v0:s.v1] = q
         return out
 
     @torch.no_grad()
-    def fwd_bwd(self, batch, q_next, batch_total=None):
+    def fwd_bwd(self, batch, q_next, batch_total=None, slices=None, q_next_ready=None):
         """Behaviour forward, TD loss against q_next, backward.  Leaves the mean gradient over the GLOBAL minibatch
         (all ranks' graphs) in the behaviour net's flat gradient buffer and returns the global loss [1] (a view of the
         reduction buffer: read or clone it before the next call).  batch_total: the global number of graphs if the
         caller knows it; otherwise it is all-reduced together with the gradient (see reduce_mean_gradient)."""
         agent = self.agent
         net = agent.gn_behaviour
-        flat = net.flat_params()
+        flat = net.flat_params(full_check=False)
         gbuf, P = self._grad_buffer()
         grad, loss = gbuf[:P], gbuf[P:P + 1]
         gbuf[P:].zero_()
@@ -200,11 +203,14 @@ class QLearner(object):
             gbuf[P + 1] = float(batch.n_graphs)
         first = True
         kept = []
-        for g0, g1 in batch.micro_ranges(self.max_edges):
-            s = _Slice(batch, g0, g1)
+        for i, (g0, g1) in enumerate(batch.micro_ranges(self.max_edges)):
+            s = slices[i] if slices is not None else _Slice(batch, g0, g1)
             x = batch.x_of(batch.cur_colour[s.v0:s.v1], s.v0, s.v1)
             _, q, self._stash = ops.gn_forward(flat, net.dims, s.packed, x, s.eattr, with_stash=True,
                                                math_mode=net.math_mode, stash=self._stash)
+            if q_next_ready is not None:              # q_next was computed on a side stream (learn_step)
+                torch.cuda.current_stream(batch.device).wait_event(q_next_ready)
+                q_next_ready = None
             _, q_exp, q_tgt, d_q = ops.td_target_loss(q, q_next[s.v0:s.v1], batch.next_colour[s.v0:s.v1], s.node_off,
                                                       batch.action[g0:g1], batch.reward[g0:g1], batch.done[g0:g1],
                                                       agent.gamma, batch_total=total, loss_out=loss)
@@ -224,11 +230,33 @@ class QLearner(object):
     @torch.no_grad()
     def learn_step(self, batch, batch_total=None):
         """dqn_agent.py:147-223 on a TransitionBatch: target forward, behaviour forward/backward,
-        fused Adam + soft target update."""
+        fused Adam + soft target update.  The micro-batch layouts are built once for both forwards.  A minibatch that is a
+        single micro-batch (the reference's 64 transitions: launch chains of ~10 us kernels that leave most SMs idle) runs
+        its target forward on a side stream next to the behaviour forward; the TD loss waits for both."""
         agent = self.agent
-        q_next = self.target_q(batch)
-        loss = self.fwd_bwd(batch, q_next, batch_total)
-        agent.gn_behaviour.optimizer.step(target_flat=agent.gn_target.flat_params(), tau=agent.tau,
+        agent.gn_behaviour.flat_params()             # one full aliasing check per step; the inner calls use the cheap one
+        agent.gn_target.flat_params()
+        ranges = batch.micro_ranges(self.max_edges)
+        slices = [_Slice(batch, g0, g1) for g0, g1 in ranges] if len(ranges) <= 2 else None
+        if len(ranges) == 1 and batch.n_edges <= (1 << 21):
+            dev = batch.device
+            main = torch.cuda.current_stream(dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+            nb = _lib.load().gcrl_gn_forward_workspace_bytes(batch.n_vertices, batch.n_edges, 0)
+            if self._side_ws is None or self._side_ws.numel() < nb:
+                self._side_ws = torch.empty(max(int(nb), 256), dtype=torch.uint8, device=dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                q_next = self.target_q(batch, slices, ws=self._side_ws)
+                ready = torch.cuda.Event()
+                ready.record(self._side)
+            q_next.record_stream(main)
+            loss = self.fwd_bwd(batch, q_next, batch_total, slices, q_next_ready=ready)
+        else:
+            q_next = self.target_q(batch, slices)
+            loss = self.fwd_bwd(batch, q_next, batch_total, slices)
+        agent.gn_behaviour.optimizer.step(target_flat=agent.gn_target.flat_params(full_check=False), tau=agent.tau,
                                           grad=agent.gn_behaviour._flat_grad)
         agent.last_loss = loss.clone()
         return agent.last_loss
