@@ -31,9 +31,20 @@ class _GraphedStep(object):
         self.ws = torch.empty(lib.gcrl_gn_forward_workspace_bytes(packed.n_vertices, packed.n_edges, 0), dtype=torch.uint8,
                               device=dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode, ws=self.ws)
-            self.action = env.step_greedy(q)
+        # capture_begin / capture_end on a side stream instead of the `torch.cuda.graph` context manager: that one
+        # synchronises, runs the garbage collector and EMPTIES the caching allocator on entry -- with tens of GB of
+        # rollout workspaces cached, a per-environment capture then cost more than the sweep it speeds up
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.graph.capture_begin()
+            try:
+                _, q, _ = ops.gn_forward(flat, net.dims, packed, env.x, eattr, math_mode=net.math_mode, ws=self.ws)
+                self.action = env.step_greedy(q)
+            finally:
+                self.graph.capture_end()
+        cur.wait_stream(side)
 
     def replay(self):
         self.graph.replay()

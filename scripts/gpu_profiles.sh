@@ -18,3 +18,8 @@ python scripts/ncu_summary.py launches gpurun_out/launches_learn64_$TAG.csv gpur
 python scripts/ncu_summary.py launches gpurun_out/launches_roll_$TAG.csv gpurun_out/${TAG}_launches_rollout_3steps_10000x50.json
 python scripts/ncu_summary.py full gpurun_out/prof_${TAG}_edge_bwd_wg.ncu-rep gpurun_out/${TAG}_ncu_full_k_edge_bwd_wg.json 20377600
 python scripts/ncu_summary.py full gpurun_out/prof_${TAG}_edge_fwd_wg.ncu-rep gpurun_out/${TAG}_ncu_full_k_edge_fwd_wg.json 20377600
+# (5) --set full of the fused vertex-side kernels (round 2) inside the same 512 x 200-vertex step
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_vertex_fwd_tc -s 1 -c 1 -o gpurun_out/prof_${TAG}_vertex_fwd -f $CMD > gpurun_out/ncu_full3.log 2>&1
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_linear_bwd_tc -s 3 -c 1 -o gpurun_out/prof_${TAG}_linear_bwd -f $CMD > gpurun_out/ncu_full4.log 2>&1
+python scripts/ncu_summary.py full gpurun_out/prof_${TAG}_vertex_fwd.ncu-rep gpurun_out/${TAG}_ncu_full_k_vertex_fwd_tc.json
+python scripts/ncu_summary.py full gpurun_out/prof_${TAG}_linear_bwd.ncu-rep gpurun_out/${TAG}_ncu_full_k_linear_bwd_tc.json
