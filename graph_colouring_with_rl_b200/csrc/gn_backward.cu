@@ -525,7 +525,8 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
-                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st);
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st,
+                       const unsigned char* img_w2, const unsigned char* img_wc);
 // gn_node_tc.cu: vertex-side products on the tensor cores
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
                int accumulate, int64_t N, cudaStream_t st, const float* dY2 = nullptr, int ngroups = 1);
@@ -533,7 +534,8 @@ int wgrad64_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const 
                int gcol0, float* gbias, int64_t N, cudaStream_t st);
 int linear_bwd_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
                   int gcol0, float* gbias, const float* W, int ldW, int wcol0, uint32_t dx_chunks, uint32_t mask_chunks,
-                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st);
+                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st,
+                  const unsigned char* wimg);
 // GCRL_VBWD_IMPL=split: the vertex side of the backward as separate weight-gradient / data-gradient launches (A/B switch)
 static bool vbwd_fused() {
     static const bool split = getenv("GCRL_VBWD_IMPL") && getenv("GCRL_VBWD_IMPL")[0] == 's';
@@ -579,6 +581,7 @@ size_t gcrl_gn_backward_workspace_bytes(int64_t N, int64_t E) {
     size_t b = 2 * align_up((size_t)E * 64 * 4);   // d e ping-pong
     b += 8 * n64;                                   // dh x2, du1, dPi, dPj, gather scratch, PNA coefficients x2
     b += align_up((size_t)N * 256 * 4);             // d agg
+    b += align_up(wimg_bytes());                    // pre-converted weight tiles (tensor-core math modes)
     return b + 256;
 }
 
@@ -614,6 +617,14 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
     float* coef_a = ar.take<float>((size_t)N * 64);
     float* coef_b = ar.take<float>((size_t)N * 64);
     float* dagg = ar.take<float>((size_t)N * 256);
+    unsigned char* wimg = ar.take<unsigned char>(wimg_bytes());
+    {
+        static const bool no_wimg = getenv("GCRL_WIMG") && getenv("GCRL_WIMG")[0] == '0';
+        if (math_mode == GCRL_MATH_FP32 || gdim != 0 || no_wimg) wimg = nullptr;
+        else RC(launch_build_weight_image(net, wimg, st));
+    }
+    const unsigned char* img_f1 = wimg ? wimg + (size_t)WIMG_F1 * WIMG_TILE_BYTES : nullptr;
+    const unsigned char* img_f2 = wimg ? wimg + (size_t)WIMG_F2 * WIMG_TILE_BYTES : nullptr;
     // gradient views, laid out like params
     auto G = [&](const float* p) { return grad + (p - params); };
 
@@ -638,9 +649,9 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             if (vbwd_fused()) {
                 // one launch per Linear layer: weight gradient, bias gradient and (masked) data gradient together
                 RC(linear_bwd_tc(x3h, dy2, S.y1, 64, 1, nullptr, 0, 0, G(hd.F2), 64, 0, G(hd.f2), hd.F2, 64, 0, 1u, 1u,
-                                 dy1, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+                                 dy1, 64, 0, 0, nullptr, 0, 0, 0, N, st, img_f2));
                 RC(linear_bwd_tc(x3h, dy1, h5, 64, 1, nullptr, 0, 0, G(hd.F1), 64, 0, G(hd.f1), hd.F1, 64, 0, 1u, 0u,
-                                 dh, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+                                 dh, 64, 0, 0, nullptr, 0, 0, 0, N, st, img_f1));
             } else {
             RC(wgrad64_tc(x3h, dy2, S.y1, 64, 1, nullptr, 0, 0, G(hd.F2), 64, 0, G(hd.f2), N, st));
             RC(dgrad64_tc(x3h, dy2, hd.F2, 64, 0, dy1, 64, 0, S.y1, 0, N, st));
@@ -695,11 +706,11 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             // update_mlp.2 and update_mlp.0, one launch each: weight + bias gradient, and the data gradient masked by the
             // stashed relu output (du1) / written to d agg's four windows and dh_{l-1}
             RC(linear_bwd_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, G(b.c2), b.U2, 64, 0, 1u, 1u,
-                             du1, 64, 0, 0, nullptr, 0, 0, 0, N, st));
+                             du1, 64, 0, 0, nullptr, 0, 0, 0, N, st, wimg_tile(wimg, l, WT_U2)));
             const int n2 = b.Dv == 64 ? 1 : 0;
             const uint32_t dx = 0xFu | ((n2 && l > 0) ? 0x10u : 0u);
             RC(linear_bwd_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, n2, G(b.U1), ldU1, 0, G(b.c1), b.U1, ldU1, 0, dx, 0u,
-                             dagg, 256, 0, 0, dh_prev, 64, 0, 0, N, st));
+                             dagg, 256, 0, 0, dh_prev, 64, 0, 0, N, st, wimg_tile(wimg, l, WT_U1)));
             if (b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
         } else if (vtc) {
             // bias gradients ride in the weight-gradient launches; d agg's four 64-column windows are one launch
@@ -734,7 +745,8 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
                                    nullptr, dPi, dp_floats, st));
             RC(launch_edge_bwd_wg(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E, S.e[l], de_cur, coef_a, coef_b,
-                                  dagg, S.amin[l], S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st));
+                                  dagg, S.amin[l], S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st,
+                                  wimg_tile(wimg, l, WT_W2), l == 0 ? nullptr : wimg_tile(wimg, l, WT_WC)));
         } else if (E > 0) {
             EdgeBwdArgs a;
             a.Pi = S.Pi[l]; a.Pj = S.Pj[l];
@@ -757,9 +769,9 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             // Pi = A h + b1 and Pj = B h: gradient of the A / B columns of message_mlp.0 and dh_{l-1} += dPi A, += dPj B
             const uint32_t dx = l > 0 ? 1u : 0u;
             RC(linear_bwd_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), b.W1, ldW1, 0, dx, 0u,
-                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st));
+                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st, wimg_tile(wimg, l, WT_WA)));
             RC(linear_bwd_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, b.W1, ldW1, 64, dx, 0u,
-                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st));
+                             dh_prev, 64, 0, 1, nullptr, 0, 0, 0, N, st, wimg_tile(wimg, l, WT_WB)));
         } else if (vtc && b.Dv == 64) {
             RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), N, st));
             RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, N, st));

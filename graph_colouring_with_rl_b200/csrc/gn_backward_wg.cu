@@ -131,6 +131,7 @@ struct BwdWgArgs {
     const int32_t* amin; const int32_t* amax;
     float* dPi; float* dPj;
     float* gW1; float* gW2; float* gb2;
+    const unsigned char* img_w2; const unsigned char* img_wc;   // pre-converted weight tiles (weight_image.cu) or null
     int dbg;                                  // timing experiments only (GCRL_WS_DBG): 16 no dPj reds, 32 no dPi reds, 2 no gather
 };
 
@@ -161,8 +162,12 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         if (!NODE) tma_prefetch_desc(&tm_de);
     }
     if (tid < 32) tmem_alloc<512>(&S.tmem_base);
-    load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, BG_N * BG_T);
-    if (!FIRST) load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, BG_N * BG_T);
+    if (a.img_w2) copy_image(S.W2, a.img_w2, 16384, tid, BG_N * BG_T);
+    else load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, BG_N * BG_T);
+    if (!FIRST) {
+        if (a.img_wc) copy_image(S.Wc, a.img_wc, 16384, tid, BG_N * BG_T);
+        else load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, BG_N * BG_T);
+    }
     float (*Cf)[64] = reinterpret_cast<float (*)[64]>(&S.Wc[0][0]);   // FIRST: C^T fp32 [d][o]
     if (FIRST) {
         for (int t = tid; t < a.De * 64; t += BG_N * BG_T) Cf[t >> 6][t & 63] = a.W1[(t & 63) * a.ldW1 + a.coff + (t >> 6)];
@@ -606,7 +611,8 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
                        const float* W1, int ldW1, int coff, const float* W2, const float* b2, const int32_t* seg_off,
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
-                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st) {
+                       float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st,
+                       const unsigned char* img_w2, const unsigned char* img_wc) {
     (void)seg_off; (void)b2;
     if (E == 0) return GCRL_OK;
     GCRL_CHECK_ARG(m != nullptr);
@@ -618,6 +624,7 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
+    a.img_w2 = img_w2; a.img_wc = img_wc;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
     CUtensorMap te, tm, tde, tout, tdpj, tdpj8;
     int rc;

@@ -31,6 +31,20 @@ __device__ __forceinline__ void gemm64(const float (*A)[LDT], const float (*W)[6
     }
 }
 
+// ---- weight image (weight_image.cu) --------------------------------------------------------------------------------------
+// Every 64 x 64 weight window the tensor-core kernels use as an MMA operand, pre-converted ONCE per network pass into the
+// bf16 hi | lo SWIZZLE_128B tile format (8 KB + 8 KB) in the caller's workspace, so that a kernel's prologue is a flat copy
+// (one L2 round trip) instead of strided fp32 loads + conversion per tile row: k_vertex_fwd_tc spent half of its ~23 us on
+// eight such tiles when the batch is small.  Tile t of block l: l * WIMG_PER_BLOCK + kind; the head's fc1 / fc2 follow.
+enum { WT_W2 = 0, WT_WC = 1, WT_U1 = 2 /* + K chunk c < 5 */, WT_U2 = 7, WT_WA = 8, WT_WB = 9, WIMG_PER_BLOCK = 10 };
+constexpr int WIMG_F1 = GCRL_N_BLOCKS * WIMG_PER_BLOCK, WIMG_F2 = WIMG_F1 + 1, WIMG_TILES = WIMG_F1 + 2;
+constexpr size_t WIMG_TILE_BYTES = 16384;
+inline size_t wimg_bytes() { return (size_t)WIMG_TILES * WIMG_TILE_BYTES; }
+inline const unsigned char* wimg_tile(const unsigned char* img, int l, int kind) {
+    return img ? img + (size_t)(l * WIMG_PER_BLOCK + kind) * WIMG_TILE_BYTES : nullptr;
+}
+int launch_build_weight_image(const NetW& net, unsigned char* img, cudaStream_t st);
+
 // Activations the backward pass needs (one carve of the caller's stash buffer).
 struct Stash {
     float* e[5];                    // e_1..e_5 [E,64]  (e_5 only in the tensor-core modes: its backward then runs as a

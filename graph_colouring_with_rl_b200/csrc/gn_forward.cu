@@ -412,17 +412,18 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
 // gn_forward_wg.cu: tensor-core edge forward, four warp groups per SM
 int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
-                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st);
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st,
+                       const unsigned char* img_w2, const unsigned char* img_wc);
 
 // dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
 int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
                          const float* e_prev, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
                          int64_t N, int64_t E, float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax,
-                         cudaStream_t st) {
+                         cudaStream_t st, const unsigned char* img_w2 = nullptr, const unsigned char* img_wc = nullptr) {
     const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
     if (math_mode != GCRL_MATH_FP32 && tc_ok)
         return launch_edge_fwd_wg(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg,
-                                  var, amin, amax, st);
+                                  var, amin, amax, st, img_w2, first ? nullptr : img_wc);
     return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
 }
 
@@ -468,7 +469,7 @@ int launch_node_update_tc(const NetW& net, int l, bool with_extra, bool x3, floa
 // gn_vertex_fwd.cu: the same vertex side as ONE launch per block (default; GCRL_VERTEX_IMPL=split keeps the launch chain)
 int launch_vertex_fwd_fused(const NetW& net, int l, bool x3, float* agg, const float* h_in, const int32_t* seg_off, int64_t N,
                             float* h_out, float* Pi, float* Pj, float* q, float* u1_buf, float* y1_buf, float* y2_buf, bool stash,
-                            cudaStream_t st);
+                            cudaStream_t st, const unsigned char* wimg);
 
 }  // namespace gcrl
 
@@ -480,6 +481,7 @@ size_t gcrl_gn_stash_bytes(int64_t N, int64_t E) { return stash_bytes(N, E); }
 
 size_t gcrl_gn_forward_workspace_bytes(int64_t N, int64_t E, int with_stash) {
     size_t b = 2 * align_up((size_t)N * 64 * 4);  // Pi, Pj
+    b += align_up(wimg_bytes());                  // pre-converted weight tiles (tensor-core math modes)
     if (!with_stash) {
         b += 2 * align_up((size_t)E * 64 * 4);    // e ping-pong
         b += 2 * align_up((size_t)N * 64 * 4);    // h ping-pong
@@ -516,6 +518,10 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
     Arena ar(ws, ws_bytes);
     float* Pi = ar.take<float>((size_t)N * 64);
     float* Pj = ar.take<float>((size_t)N * 64);
+    unsigned char* wimg = ar.take<unsigned char>(wimg_bytes());
+    static const bool no_wimg = getenv("GCRL_WIMG") && getenv("GCRL_WIMG")[0] == '0';       // A/B switch: convert in every kernel
+    if (math_mode == GCRL_MATH_FP32 || gdim != 0 || no_wimg) wimg = nullptr;
+    else if ((rc = launch_build_weight_image(net, wimg, st))) return rc;
     Stash S;
     float *eb[2] = {nullptr, nullptr}, *hb[2] = {nullptr, nullptr}, *aggb = nullptr;
     if (stash_p) {
@@ -549,7 +555,8 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         NvtxRange nv_e("edge: message MLP + PNA");
         rc = launch_edge_fwd_mode(math_mode, net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
                              seg_off, src, dst, N, E, e_out, agg, stash_p ? S.var[l] : nullptr,
-                             stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st);
+                             stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st,
+                             wimg_tile(wimg, l, WT_W2), wimg_tile(wimg, l, WT_WC));
         }
         if (rc) return rc;
         NvtxRange nv_v(last ? "vertex: update MLP + head" : "vertex: update MLP + next projections");
@@ -563,7 +570,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
             if (!vertex_split)
                 rc = launch_vertex_fwd_fused(net, l, math_mode == GCRL_MATH_BF16X3, agg, h_prev, seg_off, N, hl, Pin, Pjn, q_out,
                                              stash_p ? S.u1[l] : nullptr, stash_p ? S.y1 : nullptr, stash_p ? S.y2 : nullptr,
-                                             stash_p != nullptr, st);
+                                             stash_p != nullptr, st, wimg);
             else
             rc = launch_node_update_tc(net, l, true, math_mode == GCRL_MATH_BF16X3, agg, h_prev, seg_off, N, hl, Pin, Pjn, q_out,
                                        stash_p ? S.u1[l] : Pi, stash_p ? S.y1 : Pi, stash_p ? S.y2 : Pj, st);

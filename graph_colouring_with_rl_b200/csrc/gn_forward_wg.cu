@@ -57,6 +57,7 @@ struct FwdWgArgs {
     float* m_out;
     AggOut out;
     int item_edges;                           // target edges per work item (an item is a run of whole segments)
+    const unsigned char* img_w2; const unsigned char* img_wc;   // pre-converted weight tiles (weight_image.cu) or null
 };
 
 template <bool FIRST, bool X3, bool ARG>
@@ -75,8 +76,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
         if (a.m_out) tma_prefetch_desc(&tm_out);
     }
     if (tid < 32) tmem_alloc<512>(&S.tmem_base);
-    load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, WG_THREADS);
-    if (!FIRST) load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, WG_THREADS);
+    if (a.img_w2) copy_image(S.W2, a.img_w2, 16384, tid, WG_THREADS);
+    else load_weight_tile(a.W2, 64, 0, S.W2[0], S.W2[1], tid, WG_THREADS);
+    if (!FIRST) {
+        if (a.img_wc) copy_image(S.Wc, a.img_wc, 16384, tid, WG_THREADS);
+        else load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, WG_THREADS);
+    }
     float (*Cf)[64] = reinterpret_cast<float (*)[64]>(&S.Wc[0][0]);   // FIRST: C^T in fp32 [d][o]
     if (FIRST)
         for (int t = tid; t < a.De * 64; t += WG_THREADS) Cf[t >> 6][t & 63] = a.W1[(t & 63) * a.ldW1 + a.coff + (t >> 6)];
@@ -331,9 +336,11 @@ static int launch_wg_variant(const CUtensorMap& tin, const CUtensorMap& tout, co
 // Tensor-core edge forward, four warp groups per SM; same contract as launch_edge_fwd (gn_forward.cu).
 int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
-                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st) {
+                       float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st,
+                       const unsigned char* img_w2, const unsigned char* img_wc) {
     if (E == 0) return GCRL_OK;
     FwdWgArgs a;
+    a.img_w2 = img_w2; a.img_wc = img_wc;
     a.Pi = Pi; a.Pj = Pj; a.e_prev = e_prev; a.De = b.De;
     a.W1 = b.W1; a.ldW1 = 2 * b.Dv + b.De; a.coff = 2 * b.Dv;
     a.W2 = b.W2; a.b2 = b.b2;

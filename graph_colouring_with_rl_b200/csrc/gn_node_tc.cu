@@ -423,6 +423,7 @@ struct LinearBwdArgs {
     float* G; int ldG, gcol0;
     float* gbias;
     const float* W; int ldW, wcol0;
+    const unsigned char* wimg;             // pre-converted tile of window wcol0 (window c at + c * 16 KB) or null
     uint32_t dx_chunks, mask_chunks;       // bit c: chunk c produces dX / is masked by X_c > 0
     int acc1, acc2;                        // outputs of map o1 (chunks < n1) / o2 (chunks >= n1) are added to memory
     int ocol1, ocol2;                      // column of chunk 0 / chunk n1 inside their output matrices
@@ -460,10 +461,14 @@ __global__ void __launch_bounds__(256, 1) k_linear_bwd_tc(const __grid_constant_
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
-    for (int c = 0; c < nch; ++c)
-        if ((a.dx_chunks >> c) & 1u)
-            load_weight_tile(a.W, a.ldW, a.wcol0 + 64 * c, reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384),
-                             reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384 + 8192), tid, 256);
+    if (a.wimg) {
+        copy_image(Wsm, a.wimg, nch * 16384, tid, 256);                 // (windows without a data gradient are copied too: unused)
+    } else {
+        for (int c = 0; c < nch; ++c)
+            if ((a.dx_chunks >> c) & 1u)
+                load_weight_tile(a.W, a.ldW, a.wcol0 + 64 * c, reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384),
+                                 reinterpret_cast<__nv_bfloat16*>(Wsm + c * 16384 + 8192), tid, 256);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -626,7 +631,8 @@ __global__ void __launch_bounds__(256, 1) k_linear_bwd_tc(const __grid_constant_
 // gradients of chunks < n1 go to dX1 [N, ldo1] at column ocol1 + 64 c, those of the X2 chunks to dX2 [N, ldo2] at ocol2.
 int linear_bwd_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, const float* X2, int ld2, int n2, float* G, int ldG,
                   int gcol0, float* gbias, const float* W, int ldW, int wcol0, uint32_t dx_chunks, uint32_t mask_chunks,
-                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st) {
+                  float* dX1, int ldo1, int ocol1, int acc1, float* dX2, int ldo2, int ocol2, int acc2, int64_t N, cudaStream_t st,
+                  const unsigned char* wimg) {
     if (N == 0) return GCRL_OK;
     const int nch = n1 + n2;
     GCRL_CHECK_ARG(nch >= 1 && nch <= NODE_MAX_CHUNKS);
@@ -639,7 +645,7 @@ int linear_bwd_tc(bool x3, const float* Y, const float* X1, int ld1, int n1, con
     if ((rc = make_tmap_rows(&o2, dX2 ? dX2 : Y, N, dX2 ? ldo2 : 64))) return rc;
     LinearBwdArgs a;
     a.n1 = n1; a.n2 = n2; a.G = G; a.ldG = ldG; a.gcol0 = gcol0; a.gbias = gbias;
-    a.W = W; a.ldW = ldW; a.wcol0 = wcol0; a.dx_chunks = dx_chunks; a.mask_chunks = mask_chunks;
+    a.W = W; a.ldW = ldW; a.wcol0 = wcol0; a.wimg = dx_chunks ? wimg : nullptr; a.dx_chunks = dx_chunks; a.mask_chunks = mask_chunks;
     a.acc1 = acc1; a.acc2 = acc2; a.ocol1 = ocol1; a.ocol2 = ocol2; a.N = N;
     const int smem = nch * 16384 + 2 * 32768 + 2 * 32768 + 64 + 256 + 1024;
     static int max_set[2] = {0, 0};

@@ -35,6 +35,8 @@ struct VertexFwdArgs {
     const int32_t* seg_off; float* agg;
     float* q;
     int store_u1, store_y;                      // write the activations the backward needs
+    const unsigned char* img_u;                 // pre-converted tiles U1 chunk 0..4 | U2 (six consecutive tiles) or null
+    const unsigned char* img_3a; const unsigned char* img_3b;   // tiles of W3a / W3b or null
     int64_t N;
 };
 
@@ -104,18 +106,34 @@ __global__ void __launch_bounds__(256, 1) k_vertex_fwd_tc(const __grid_constant_
         tma_prefetch_desc(&t_ho);
     }
     if (warp == 0) tmem_alloc<256>(tmem_slot);
-    for (int c = 0; c < a.nch; ++c)
-        load_weight_tile(a.U1, a.ldU1, 64 * c, reinterpret_cast<__nv_bfloat16*>(W1s + c * 16384),
-                         reinterpret_cast<__nv_bfloat16*>(W1s + c * 16384 + 8192), tid, 256);
-    load_weight_tile(a.U2, 64, 0, reinterpret_cast<__nv_bfloat16*>(W2s), reinterpret_cast<__nv_bfloat16*>(W2s + 8192), tid, 256);
+    if (a.img_u) {
+        copy_image(W1s, a.img_u, VF_W1_BYTES + VF_W2_BYTES, tid, 256);      // U1 chunks 0..4 | U2: contiguous in the image and here
+    } else {
+        for (int c = 0; c < a.nch; ++c)
+            load_weight_tile(a.U1, a.ldU1, 64 * c, reinterpret_cast<__nv_bfloat16*>(W1s + c * 16384),
+                             reinterpret_cast<__nv_bfloat16*>(W1s + c * 16384 + 8192), tid, 256);
+        load_weight_tile(a.U2, 64, 0, reinterpret_cast<__nv_bfloat16*>(W2s), reinterpret_cast<__nv_bfloat16*>(W2s + 8192), tid, 256);
+    }
     if (LAST) {          // F1 tile | F2 tile, each hi 8 KB | lo 8 KB
-        load_weight_tile(a.W3a, a.ldW3a, a.col3a, reinterpret_cast<__nv_bfloat16*>(W3s), reinterpret_cast<__nv_bfloat16*>(W3s + 8192), tid, 256);
-        load_weight_tile(a.W3b, a.ldW3b, a.col3b, reinterpret_cast<__nv_bfloat16*>(W3s + 16384),
-                         reinterpret_cast<__nv_bfloat16*>(W3s + 16384 + 8192), tid, 256);
+        if (a.img_3a) {
+            copy_image(W3s, a.img_3a, 16384, tid, 256);
+            copy_image(W3s + 16384, a.img_3b, 16384, tid, 256);
+        } else {
+            load_weight_tile(a.W3a, a.ldW3a, a.col3a, reinterpret_cast<__nv_bfloat16*>(W3s), reinterpret_cast<__nv_bfloat16*>(W3s + 8192), tid, 256);
+            load_weight_tile(a.W3b, a.ldW3b, a.col3b, reinterpret_cast<__nv_bfloat16*>(W3s + 16384),
+                             reinterpret_cast<__nv_bfloat16*>(W3s + 16384 + 8192), tid, 256);
+        }
     } else {             // one 128-row tile: rows 0-63 = A, rows 64-127 = B; hi 16 KB | lo 16 KB
-        load_weight_tile(a.W3a, a.ldW3a, a.col3a, reinterpret_cast<__nv_bfloat16*>(W3s), reinterpret_cast<__nv_bfloat16*>(W3s + 16384), tid, 256);
-        load_weight_tile(a.W3b, a.ldW3b, a.col3b, reinterpret_cast<__nv_bfloat16*>(W3s + 8192),
-                         reinterpret_cast<__nv_bfloat16*>(W3s + 16384 + 8192), tid, 256);
+        if (a.img_3a) {
+            copy_image(W3s, a.img_3a, 8192, tid, 256);                      // A hi
+            copy_image(W3s + 16384, a.img_3a + 8192, 8192, tid, 256);       // A lo
+            copy_image(W3s + 8192, a.img_3b, 8192, tid, 256);               // B hi
+            copy_image(W3s + 24576, a.img_3b + 8192, 8192, tid, 256);       // B lo
+        } else {
+            load_weight_tile(a.W3a, a.ldW3a, a.col3a, reinterpret_cast<__nv_bfloat16*>(W3s), reinterpret_cast<__nv_bfloat16*>(W3s + 16384), tid, 256);
+            load_weight_tile(a.W3b, a.ldW3b, a.col3b, reinterpret_cast<__nv_bfloat16*>(W3s + 8192),
+                             reinterpret_cast<__nv_bfloat16*>(W3s + 16384 + 8192), tid, 256);
+        }
     }
     if (tid < 64) {
         c1_s[tid] = a.c1[tid];
@@ -352,7 +370,7 @@ static int launch_vertex_variant(const CUtensorMap* tm, const VertexFwdArgs& a, 
 // (gn_node_tc.cu).  stash: u1 / y1 / y2 are wanted by the backward (else the three buffers are ignored).
 int launch_vertex_fwd_fused(const NetW& net, int l, bool x3, float* agg, const float* h_in, const int32_t* seg_off, int64_t N,
                             float* h_out, float* Pi, float* Pj, float* q, float* u1_buf, float* y1_buf, float* y2_buf, bool stash,
-                            cudaStream_t st) {
+                            cudaStream_t st, const unsigned char* wimg) {
     if (N == 0) return GCRL_OK;
     const BlockW& b = net.blk[l];
     const bool last = l == GCRL_N_BLOCKS - 1;
@@ -362,6 +380,9 @@ int launch_vertex_fwd_fused(const NetW& net, int l, bool x3, float* agg, const f
     a.seg_off = seg_off; a.agg = agg; a.q = q; a.N = N;
     a.store_u1 = stash ? 1 : 0; a.store_y = (stash && last) ? 1 : 0;
     a.F3 = nullptr; a.f3 = nullptr;
+    a.img_u = wimg_tile(wimg, l, WT_U1);
+    a.img_3a = wimg ? (last ? wimg + (size_t)WIMG_F1 * WIMG_TILE_BYTES : wimg_tile(wimg, l + 1, WT_WA)) : nullptr;
+    a.img_3b = wimg ? (last ? wimg + (size_t)WIMG_F2 * WIMG_TILE_BYTES : wimg_tile(wimg, l + 1, WT_WB)) : nullptr;
     if (last) {
         a.W3a = net.head.F1; a.ldW3a = 64; a.col3a = 0; a.W3b = net.head.F2; a.ldW3b = 64; a.col3b = 0;
         a.b3a = net.head.f1; a.b3b = net.head.f2; a.F3 = net.head.F3; a.f3 = net.head.f3;

@@ -344,6 +344,21 @@ __device__ __forceinline__ void load_weight_tile(const float* W, int ld, int col
     }
 }
 
+// flat global -> shared copy of a pre-converted weight image (multiples of 16 bytes), eight 16-byte loads in flight per thread:
+// ONE L2 round trip per batch instead of one per tile row of in-kernel conversion (weight_image.cu)
+__device__ __forceinline__ void copy_image(void* smem_dst, const unsigned char* gsrc, int nbytes, int tid, int nthreads) {
+    const uint4* src = reinterpret_cast<const uint4*>(gsrc);
+    uint4* dst = reinterpret_cast<uint4*>(smem_dst);
+    const int n = nbytes >> 4;
+    for (int t0 = tid; t0 < n; t0 += 8 * nthreads) {
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (t0 + k * nthreads < n) v[k] = __ldg(src + t0 + k * nthreads);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (t0 + k * nthreads < n) dst[t0 + k * nthreads] = v[k];
+    }
+}
+
 // 8 floats -> bf16 chunk(s) of an operand tile at (row, chunk cb)
 template <bool X3>
 __device__ __forceinline__ void store_split8(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int row, int cb) {
