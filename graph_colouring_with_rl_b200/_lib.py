@@ -113,15 +113,22 @@ def require_cuda(t, name='tensor'):
 
 
 def ptr(t):
-    """Raw device pointer of a contiguous tensor (None -> NULL)."""
+    """Raw device pointer of a contiguous tensor (None -> NULL); a plain int, which ctypes takes for a void*."""
     if t is None:
         return None
     assert t.is_contiguous(), 'non-contiguous tensor passed to the C ABI'
-    return c_void_p(t.data_ptr())
+    return t.data_ptr()
+
+
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
 
 
 def stream_ptr(device=None):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """cudaStream_t of torch's current stream on `device` (the raw-handle fast path when this torch has it: a learn step
+    at the reference's minibatch size makes ~15 library calls and is bound by host issue time)."""
+    if _raw_stream is not None and device is not None and getattr(device, 'index', None) is not None:
+        return _raw_stream(device.index)
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 class _NoGuard(object):

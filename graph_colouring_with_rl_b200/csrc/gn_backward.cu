@@ -542,6 +542,36 @@ static bool vbwd_fused() {
     return !split;
 }
 
+// Block 1's narrow weight gradients in one launch (its vertex features are Dv <= 8 wide, so these are [64 x Dv] blocks that the
+// tensor-core kernels do not cover): G_m[o][col_m + d] += sum_r Y_m[r][o] x[r][d] for up to three (Y_m, G_m, col_m) and
+// gbias[o] += sum_r Y_b[r][o] for Y_b = Y of matrix `bias_m` -- instead of three split-K SGEMM launches and a column sum.
+struct NarrowWgradArgs {
+    const float* Y[3]; float* G[3]; int ldG[3], col[3];
+    int nmat, bias_m;
+    float* gbias;
+    const float* x; int Dv;
+    int64_t N;
+};
+__global__ void __launch_bounds__(192) k_narrow_wgrad(const NarrowWgradArgs a) {
+    pdl_prologue();
+    const int m = threadIdx.x >> 6, o = threadIdx.x & 63;
+    if (m >= a.nmat) return;
+    float acc[8], bs = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[d] = 0.f;
+    const float* Y = a.Y[m];
+    for (int64_t r = blockIdx.x; r < a.N; r += gridDim.x) {
+        const float y = Y[r * 64 + o];
+        bs += y;
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (d < a.Dv) acc[d] = fmaf(y, a.x[r * a.Dv + d], acc[d]);
+    }
+    float* g = a.G[m] + (int64_t)o * a.ldG[m] + a.col[m];
+    for (int d = 0; d < a.Dv; ++d) atomicAdd(g + d, acc[d]);
+    if (a.gbias && m == a.bias_m) atomicAdd(a.gbias + o, bs);
+}
+
 // first stage of the head's backward (architecture.py:197 fc3 and the ReLU in front of it) in one launch:
 //   dy2[r][k] = dq[r] F3[k] [y2[r][k] > 0],   gF3[k] += sum_r dq[r] y2[r][k],   gf3 += sum_r dq[r]
 __global__ void __launch_bounds__(256) k_head_bwd_first(const float* __restrict__ dq, const float* __restrict__ y2,
@@ -711,7 +741,7 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             const uint32_t dx = 0xFu | ((n2 && l > 0) ? 0x10u : 0u);
             RC(linear_bwd_tc(x3, du1, S.agg[l], 256, 4, h_prev, 64, n2, G(b.U1), ldU1, 0, G(b.c1), b.U1, ldU1, 0, dx, 0u,
                              dagg, 256, 0, 0, dh_prev, 64, 0, 0, N, st, wimg_tile(wimg, l, WT_U1)));
-            if (b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
+            // (block 1's narrow tail of U1 joins the dPi / dPj ones in k_narrow_wgrad after the edge kernel)
         } else if (vtc) {
             // bias gradients ride in the weight-gradient launches; d agg's four 64-column windows are one launch
             RC(wgrad64_tc(x3, dh, S.u1[l], 64, 1, nullptr, 0, 0, G(b.U2), 64, 0, G(b.c2), N, st));
@@ -775,7 +805,17 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
         } else if (vtc && b.Dv == 64) {
             RC(wgrad64_tc(x3, dPi, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 0, G(b.b1), N, st));
             RC(wgrad64_tc(x3, dPj, h_prev, 64, 1, nullptr, 0, 0, G(b.W1), ldW1, 64, nullptr, N, st));
+        } else if (vtc && vbwd_fused() && b.Dv <= 8) {
+            NarrowWgradArgs na;
+            na.Y[0] = dPi; na.G[0] = G(b.W1); na.ldG[0] = ldW1; na.col[0] = 0;
+            na.Y[1] = dPj; na.G[1] = G(b.W1); na.ldG[1] = ldW1; na.col[1] = b.Dv;
+            na.Y[2] = du1; na.G[2] = G(b.U1); na.ldG[2] = ldU1; na.col[2] = 256;
+            na.nmat = 3; na.bias_m = 0; na.gbias = G(b.b1); na.x = h_prev; na.Dv = b.Dv; na.N = N;
+            int64_t blocks = N < (int64_t)sm_count() * 4 ? N : (int64_t)sm_count() * 4;
+            launch_k(k_narrow_wgrad, dim3((int)blocks), dim3(192), 0, st, na);
+            GCRL_LAUNCH_CHECK();
         } else {
+            if (vtc && vbwd_fused() && b.Dv != 64) RC(wgrad(du1, 64, 64, h_prev, b.Dv, b.Dv, G(b.U1), ldU1, 256, N, st));
             RC(wgrad(dPi, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, 0, N, st));
             RC(wgrad(dPj, 64, 64, h_prev, b.Dv, b.Dv, G(b.W1), ldW1, b.Dv, N, st));
             RC(colsum(dPi, N, 64, G(b.b1), st));
