@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                                                                const __grid_constant__ CUtensorMap tm_out,
                                                                const __grid_constant__ CUtensorMap tm_dpj,
                                                                const __grid_constant__ CUtensorMap tm_dpj8,
+                                                               const __grid_constant__ CUtensorMap tm_dpi,
                                                                const BwdWgArgs a) {
     pdl_prologue();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -519,9 +520,11 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 const float s1 = warp_colsum32(dz, lane);
                 atomicAdd(a.dPi + (int64_t)d1 * 64 + 32 * half + lane, s1);
             } else if (valid) {
-                float* pi = a.dPi + (int64_t)my_dst * 64 + 32 * half;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) red_add_v4(pi + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+                // three or more segments inside these 32 rows (graphs of a few dozen vertices: the reference's training
+                // shapes): the row goes out as a one-row TMA reduce from the fp32 staging tile, like dPj -- eight 16-byte LSU
+                // reds per lane here made this phase 6-16 k cycles of a 35 k-cycle tile on 15-50-vertex minibatches
+                tma_reduce_add_2d(&tm_dpi, 32 * half, my_dst, B3 + half * 16384 + row * 128);
+                bulk_commit();
             }
         }
         BW_TR(11);
@@ -594,14 +597,15 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
 
 template <bool FIRST, bool NODE, bool X3>
 static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, const CUtensorMap& tde, const CUtensorMap& tout,
-                                 const CUtensorMap& tdpj, const CUtensorMap& tdpj8, const BwdWgArgs& a, int grid, cudaStream_t st) {
+                                 const CUtensorMap& tdpj, const CUtensorMap& tdpj8, const CUtensorMap& tdpi, const BwdWgArgs& a, int grid,
+                                 cudaStream_t st) {
     const int smem = (int)sizeof(BwdWgSmem) + 1024;
     static bool done = false;
     if (!done) {
         GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    launch_k(k_edge_bwd_wg<FIRST, NODE, X3>, dim3(grid), dim3(BG_N * BG_T), smem, st, te, tm, tde, tout, tdpj, tdpj8, a);
+    launch_k(k_edge_bwd_wg<FIRST, NODE, X3>, dim3(grid), dim3(BG_N * BG_T), smem, st, te, tm, tde, tout, tdpj, tdpj8, tdpi, a);
     return GCRL_OK;
 }
 
@@ -626,7 +630,7 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
     a.img_w2 = img_w2; a.img_wc = img_wc;
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
-    CUtensorMap te, tm, tde, tout, tdpj, tdpj8;
+    CUtensorMap te, tm, tde, tout, tdpj, tdpj8, tdpi;
     int rc;
     // unused maps point at a valid [N,64] array so that encoding never fails
     if ((rc = make_tmap_rows64(&te, first ? Pi : e_prev, first ? N : E, 128))) return rc;
@@ -635,16 +639,17 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     if ((rc = make_tmap_rows64(&tout, first ? Pi : de_prev, first ? N : E, 128))) return rc;
     if ((rc = make_tmap_rows64(&tdpj, dPj, N, 1))) return rc;
     if ((rc = make_tmap_rows64(&tdpj8, dPj, N, 8))) return rc;
+    if ((rc = make_tmap_rows64(&tdpi, dPi, N, 1))) return rc;
     const int64_t tiles = (E + TILE - 1) / TILE;
     const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
     const int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (no_de ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
-    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
-                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
-    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
-                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
-    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st)
-                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, tdpj, tdpj8, a, (int)grid, st);
+    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
+                       : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);
+    else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
+                            : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);
+    else rc = x3 ? launch_bwd_wg_variant<false, false, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
+                 : launch_bwd_wg_variant<false, false, false>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);
     prof_end(tok, st);
     if (rc) return rc;
     GCRL_LAUNCH_CHECK();
