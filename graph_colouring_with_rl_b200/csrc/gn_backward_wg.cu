@@ -523,8 +523,14 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 // three or more segments inside these 32 rows (graphs of a few dozen vertices: the reference's training
                 // shapes): the row goes out as a one-row TMA reduce from the fp32 staging tile, like dPj -- eight 16-byte LSU
                 // reds per lane here made this phase 6-16 k cycles of a 35 k-cycle tile on 15-50-vertex minibatches
+#ifdef GCRL_DPI_LSU        // A/B build: the LSU reds this path used before
+                float* pi = a.dPi + (int64_t)my_dst * 64 + 32 * half;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) red_add_v4(pi + 4 * c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+#else
                 tma_reduce_add_2d(&tm_dpi, 32 * half, my_dst, B3 + half * 16384 + row * 128);
                 bulk_commit();
+#endif
             }
         }
         BW_TR(11);
