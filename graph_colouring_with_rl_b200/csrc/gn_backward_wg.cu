@@ -382,7 +382,13 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
 #pragma unroll
             for (int it = 0; it < 8; ++it) x[it] = *reinterpret_cast<const float4*>(l_ptr(B1f, (gt >> 4) + 16 * it, c4));
         }
+#ifdef GCRL_CONVERT_NAMED_SYNC
         named_sync(bar_id, BG_T);          // every landing row has been read before any operand row is written
+#else
+        // Row r of an operand tile overwrites exactly row r of the landing tile (hi: first slab, lo: second), and the 16 threads
+        // that read a row (one half-warp) are the ones that write it: a warp barrier replaces the group-wide one (-1 %)
+        __syncwarp();
+#endif
         BW_TR(5);
 #pragma unroll
         for (int it = 0; it < 8; ++it) {

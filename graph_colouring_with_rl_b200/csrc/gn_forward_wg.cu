@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
         Carry carry;
         carry.dst = -1;
         stat_init(carry.s);
+        bool chain_pending = false;                // the previous tile's partials still wait in the reducer scratch
+        int prev_nrows = 0;
         if (!FIRST && lt == 0 && e0 < e1) {
             mbar_arrive_expect_tx(bar_tma, 128 * 64 * 4);
             tma_load_2d(T, &tm_in, 0, e0, bar_tma);
@@ -154,6 +156,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 float2 ya[8], yb[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) { ya[c] = __ldg(pja + 4 * c); yb[c] = __ldg(pjb + 4 * c); }
+#ifndef GCRL_FWD_CHAIN_AT_END
+                // the previous tile's carry chain (64 threads: a few dozen dependent shared-memory reads, the occasional
+                // aggregate write) runs here, under the first fragment group's Pj rows in flight, instead of at the end of
+                // its own tile where the other two warps idled at the next top-of-tile barrier
+                if (g == 0 && chain_pending) {
+                    if (lt < 64) tile_reduce_chain_t(prev_nrows, red, carry, a.out, lt);
+                    chain_pending = false;
+                }
+#endif
                 if (va && da != cur_d) {          // new segment: refresh the cached Pi row
                     cur_d = da;
                     const float2* pia = reinterpret_cast<const float2*>(a.Pi + (int64_t)da * 64 + cp);
@@ -202,7 +213,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                     const int t = k * 128 + lt;
                     x[k] = *reinterpret_cast<const float4*>(l_ptr(M, t >> 4, t & 15));
                 }
-                named_sync(bar_id, 128);           // every row has been read before any operand row is written
+                // every row has been read before any operand row is written.  (A row's 16 readers -- one half-warp -- are also its
+                // writers, so a warp barrier would do, and it does in the backward; here it measured 10 % SLOWER, 3.70 vs 3.34 ms
+                // per launch: the group-wide barrier keeps the four warps' conversion bursts from interleaving with other groups')
+                named_sync(bar_id, 128);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int t = k * 128 + lt;
@@ -300,13 +314,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 tma_load_2d(T + 16384, &tm_in, 32, t0 + TILE, bar_tma);
             }
             FW_TR(9);
+#ifdef GCRL_FWD_CHAIN_AT_END
             if (lt < 64) tile_reduce_chain_t(nrows, red, carry, a.out, lt);
+#else
+            chain_pending = true;
+            prev_nrows = nrows;
+#endif
             FW_TR(10);
 #ifdef GCRL_FWD_TRACE_BUILD
             ++tr_tiles;
 #endif
         }
-        if (lt < 64) carry_flush_t(carry, a.out, lt);
+        if (lt < 64) {
+            if (chain_pending) tile_reduce_chain_t(prev_nrows, red, carry, a.out, lt);
+            carry_flush_t(carry, a.out, lt);
+        }
         named_sync(bar_id, 128);   // reducer scratch quiescent before the next item
     }
 #ifdef GCRL_FWD_TRACE_BUILD
