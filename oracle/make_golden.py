@@ -120,11 +120,11 @@ def stage_train(ref, ds, episodes=160):
     print('train: saved', path)
 
 
-def _load_agent(ref, weights=True):
+def _load_agent(ref, weights=True, root='parity_weights'):
     torch.manual_seed(0)
     agent = ref.dqn_agent.DQNAgentGN(2, 1, 0)
     if weights:
-        agent.load_models(os.path.join(GOLD, 'parity_weights'))
+        agent.load_models(os.path.join(GOLD, root))
         agent.soft_update(agent.gn_behaviour, agent.gn_target, 1)
     return agent
 
@@ -263,11 +263,20 @@ def _ordered_sample(mem, n):
             mem.done_memory[idx])
 
 
-def stage_rollouts(ref, ds):
+def stage_rollouts_trained25k(ref, ds):
+    """The same rollouts with FULLY trained weights: tests/golden/trained25k_GN is the behaviour network after the
+    reference's whole 25 000-episode schedule run by this repository's device training loop on a B200
+    (scripts/train_full_schedule.py, profiles/r02_train_full_schedule.json) -- the closest available stand-in for the
+    reference's missing trained_policies/learned_parameters_GN.  Here the UNMODIFIED reference plays them on its 100
+    validation graphs on the CPU; tests/test_trained_policy_gpu.py replays them on the device."""
+    stage_rollouts(ref, ds, root='trained25k', out='rollouts_trained25k.npz')
+
+
+def stage_rollouts(ref, ds, root='parity_weights', out='rollouts.npz'):
     """Reference greedy rollouts (test_policy_functions.test_using_learned_policy) with the
     trained weights on all 100 validation graphs: vertex sequences, colours used, and the
     top-2 Q gap at every NN-chosen step."""
-    agent = _load_agent(ref, True)
+    agent = _load_agent(ref, True, root)
     seqs, gaps = [], []
     cur = {'seq': None}
     EnvCls = ref.env.GraphColouring
@@ -296,10 +305,10 @@ def stage_rollouts(ref, ds):
         gaps.append(np.asarray(cur['gaps'], dtype=np.float32))
     EnvCls.step = orig_step
     np.savez_compressed(
-        os.path.join(GOLD, 'rollouts.npz'), colours_used=np.asarray(used, dtype=np.int32),
+        os.path.join(GOLD, out), colours_used=np.asarray(used, dtype=np.int32),
         seq=np.concatenate(seqs), seq_len=np.asarray([len(s) for s in seqs], dtype=np.int32),
         gaps=np.concatenate(gaps), gaps_len=np.asarray([len(g) for g in gaps], dtype=np.int32),
-        provenance=np.asarray('oracle/make_golden.py stage_rollouts: reference test_using_learned_policy, parity_weights_GN'))
+        provenance=np.asarray('oracle/make_golden.py stage_rollouts: reference test_using_learned_policy, %s_GN' % root))
     print('rollouts: mean colours %.3f in %.0fs' % (np.mean(used), time.time() - t0))
 
 

@@ -6,7 +6,7 @@ Watts-Strogatz / Barabasi-Albert graphs from networkx stand in for its seven fam
 the reference's OWN 100 validation graphs (tests/golden/validation_graphs.npz), whose DSATUR colour counts (mean 7.42) and
 random-order counts (mean 8.58) are the yardsticks.
 
-    python scripts/train_full_schedule.py [episodes] [math_mode] > profiles/r02_train_full_schedule.json
+    python scripts/train_full_schedule.py [episodes] [math_mode] [weights_root] > profiles/r02_train_full_schedule.json
 """
 import contextlib
 import json
@@ -62,6 +62,9 @@ def main():
         tr.run(episodes, verbose=True, log_every=2500)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+    if len(sys.argv) > 3:                                 # save the trained behaviour network (the reference's <root>_GN state_dict blob)
+        with contextlib.redirect_stdout(sys.stderr):
+            agent.save_models(sys.argv[3])
     curve = {int(ep): float(np.mean(v.colours_used)) for ep, v in sorted(tr.all_validation_stats.items())}
     losses = [float(l.item()) for l in tr.losses[::max(1, len(tr.losses) // 50)]]
     res = {'episodes': episodes, 'math_mode': math_mode, 'wall_s': dt, 'episodes_per_sec': episodes / dt, 'env_steps': tr.t_step,
