@@ -140,6 +140,33 @@ def test_rollouts_match_reference():
             assert used == int(d['colours_used'][gi])
 
 
+def test_rollouts_with_fully_trained_weights_match_reference():
+    """The same pin on the FULLY trained policy (tests/golden/trained25k_GN: the reference's 25 000-episode schedule run by the
+    device training loop; rollouts_trained25k.npz: what the unmodified reference does with it)."""
+    import os
+    from collections import OrderedDict
+    d = np.load(util.GOLD + '/rollouts_trained25k.npz')
+    sd = torch.load(os.path.join(util.GOLD, 'trained25k_GN'), map_location='cpu')
+    p = OrderedDict((k, v.float()) for k, v in sd.items())
+    seqs = util.split_by(d['seq'], d['seq_len'])
+    gaps = util.split_by(d['gaps'], d['gaps_len'])
+    checked = 0
+    for gi in range(2, 100, 8):
+        g = GRAPHS[gi]
+
+        def q_fn(col, g=g):
+            x, ei, ea = gn_oracle.observation(g['adj'], col, g['edge_list'])
+            with torch.no_grad():
+                return gn_oracle.gn_forward(p, x, ei, ea)[1].view(-1).numpy()
+        used, seq, col, og = env_oracle.greedy_rollout(g['adj'], q_fn, g['edge_list'])
+        if gaps[gi].size == 0 or gaps[gi].min() > 1e-5:
+            assert seq == [int(v) for v in seqs[gi]], g['name']
+            assert used == int(d['colours_used'][gi])
+            checked += 1
+    assert checked >= 8
+    assert abs(float(d['colours_used'].mean()) - 7.45) < 1e-9      # (DSATUR on the same graphs: 7.42, random order: 8.58)
+
+
 def test_replay_oracle_matches_reference_replay_buffer():
     """oracle/replay_oracle.py against the reference ReplayBuffer (tests/golden/replay_buffer.npz): ring index, wrap-around
     and the minibatches three seeded sample_buffer calls returned."""
