@@ -14,12 +14,23 @@ pytestmark = pytest.mark.gpu
 WEIGHTS_ROOT = os.path.join(util.GOLD, 'parity_weights')
 
 
-def make_agent(math_mode='fp32'):
+def make_agent(math_mode='fp32', root=WEIGHTS_ROOT):
     from graph_colouring_with_rl_b200.dqn_agent import DQNAgentGN
     torch.manual_seed(0)
     agent = DQNAgentGN(2, 1, 0, test_mode=True, math_mode=math_mode)
-    agent.load_models(WEIGHTS_ROOT)
+    agent.load_models(root)
     return agent
+
+
+def load_weights(which):
+    """'parity': the reference agent's own state_dict after 160 CPU episodes; 'trained25k': the behaviour network after the
+    reference's whole 25 000-episode schedule run by the device training loop (scripts/train_full_schedule.py)."""
+    if which == 'parity':
+        return WEIGHTS_ROOT, util.load_parity_weights()
+    from collections import OrderedDict
+    root = os.path.join(util.GOLD, 'trained25k')
+    sd = torch.load(root + '_GN', map_location='cpu')
+    return root, OrderedDict((k, v.float()) for k, v in sd.items())
 
 
 def oracle_q(params, adj, colour):
@@ -29,8 +40,9 @@ def oracle_q(params, adj, colour):
     return q.view(-1).numpy()
 
 
+@pytest.mark.parametrize('weights', ['parity', 'trained25k'])
 @pytest.mark.parametrize('math_mode,tol', [('fp32', 5e-5), ('bf16x3', 1e-4)])
-def test_lemos_reconstructible_rollouts_vs_oracle(math_mode, tol):
+def test_lemos_reconstructible_rollouts_vs_oracle(math_mode, tol, weights):
     """Greedy rollouts (first-vertex rule, argmax Q, first fit, leaf pass) on queen / Mycielski graphs:
     the device sequence equals the oracle's up to the first decision whose top-2 Q gap is below 4*tol;
     every colouring is proper and complete."""
@@ -39,8 +51,10 @@ def test_lemos_reconstructible_rollouts_vs_oracle(math_mode, tol):
     from graph_colouring_with_rl_b200.rollouts import greedy_rollouts, sequences_from_actions
     names = ['queen5_5', 'queen6_6', 'queen7_7', 'queen8_8', 'queen8_12', 'queen10_10', 'myciel5', 'myciel6']
     graphs = lemos_reconstructible(names)
-    agent = make_agent(math_mode)
-    params = util.load_parity_weights()
+    root, params = load_weights(weights)
+    agent = make_agent(math_mode, root)
+    if weights == 'trained25k' and math_mode == 'bf16x3':
+        tol = 3e-4                          # |dQ| of bf16x3 on fully trained weights (|Q| up to ~10 on the 100-vertex boards)
     res = greedy_rollouts([a for _, a in graphs], agent.gn_behaviour, record=True)
     seqs = sequences_from_actions(res['actions'])
     used = res['colours_used'].cpu().numpy()
@@ -65,7 +79,8 @@ def test_lemos_reconstructible_rollouts_vs_oracle(math_mode, tol):
         lower = max(QUEEN_BOARDS[nm]) if nm in QUEEN_BOARDS else MYCIEL_ORDER[nm]
         assert used[i] >= lower, nm
     # the boards are highly symmetric, so near-ties are common: count the decisions that could be compared
-    print('%s: %d graphs compared to the end, %d decisions compared in total' % (math_mode, full, checked))
+    print('%s / %s weights: %d graphs compared to the end, %d decisions compared in total; colours used %s'
+          % (math_mode, weights, full, checked, dict(zip(names, used.tolist()))))
     assert full >= 1 and checked >= 40
     targets = lemos_reconstructible(names[:3], as_targets=True)
     stats, by = run_learned_policy_on_dataset(targets, agent)
