@@ -526,7 +526,8 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st,
-                       const unsigned char* img_w2, const unsigned char* img_wc);
+                       const unsigned char* img_w2, const unsigned char* img_wc, const float* x_first, const float* b1,
+                       int Dv);
 // gn_node_tc.cu: vertex-side products on the tensor cores
 int dgrad64_tc(bool x3, const float* dY, const float* W, int ldw, int wcol, float* dX, int ldx, int xcol, const float* mask,
                int accumulate, int64_t N, cudaStream_t st, const float* dY2 = nullptr, int ngroups = 1);
@@ -776,7 +777,8 @@ int gcrl_gn_backward(const float* params, int vdim, int edim, int gdim, int64_t 
             RC(launch_edge_bwd_wg(l == 0, math_mode == GCRL_MATH_BF16X3, S.Pi[l], S.Pj[l], (l == 0) ? eattr : S.e[l - 1],
                                   b.De, b.W1, ldW1, 2 * b.Dv, b.W2, b.b2, seg_off, src, dst, N, E, S.e[l], de_cur, coef_a, coef_b,
                                   dagg, S.amin[l], S.amax[l], de_prev, dPi, dPj, G(b.W1), G(b.W2), G(b.b2), st,
-                                  wimg_tile(wimg, l, WT_W2), l == 0 ? nullptr : wimg_tile(wimg, l, WT_WC)));
+                                  wimg_tile(wimg, l, WT_W2), l == 0 ? nullptr : wimg_tile(wimg, l, WT_WC),
+                                  l == 0 ? x : nullptr, b.b1, b.Dv));
         } else if (E > 0) {
             EdgeBwdArgs a;
             a.Pi = S.Pi[l]; a.Pj = S.Pj[l];

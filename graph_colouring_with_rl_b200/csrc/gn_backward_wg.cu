@@ -32,6 +32,8 @@ namespace gcrl {
 
 using namespace tc;
 
+bool first_direct_ok(int Dv, int De, const float* x);      // gn_forward_wg.cu
+
 // phase timeline of group 0 of CTA 0 (diagnostic build: GCRL_NVCC_FLAGS=-DGCRL_BWD_TRACE_BUILD): cycles per phase
 // averaged over the group's tiles, printed at the end of the kernel
 #ifdef GCRL_BWD_TRACE_BUILD
@@ -124,6 +126,7 @@ struct BwdWgArgs {
     const float* e_prev; int De;
     const float* W1; int ldW1, coff;
     const float* W2;
+    const float* x; const float* b1;          // DIRECT (block 1 with 2 vertex features + 1 edge feature): raw inputs
     const int32_t* src; const int32_t* dst;
     int32_t N, E;
     const float* ca; const float* cb;
@@ -136,7 +139,9 @@ struct BwdWgArgs {
 };
 
 // FIRST: block 1 (raw edge features, no d e_0).  NODE: block 5 (no d e_5: dm = ca + cb e_5 + arg terms).
-template <bool FIRST, bool NODE, bool X3>
+// DIRECT (FIRST only; Dv = 2, De = 1): hid and its relu mask are re-evaluated from the row's five input scalars in
+// epilogue 1, in the forward's operation order (gn_forward_wg.cu), instead of gathering Pi[dst] + Pj[src] into TMEM.
+template <bool FIRST, bool NODE, bool X3, bool DIRECT = false>
 __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_constant__ CUtensorMap tm_e,
                                                                const __grid_constant__ CUtensorMap tm_m,
                                                                const __grid_constant__ CUtensorMap tm_de,
@@ -170,7 +175,16 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         else load_weight_tile(a.W1, a.ldW1, a.coff, S.Wc[0], S.Wc[1], tid, BG_N * BG_T);
     }
     float (*Cf)[64] = reinterpret_cast<float (*)[64]>(&S.Wc[0][0]);   // FIRST: C^T fp32 [d][o]
+    // DIRECT: per output column o, (A[o][0], A[o][1], B[o][0], B[o][1]) and (C[o][0], b1[o])
+    float4* const wA = reinterpret_cast<float4*>(&S.Wc[0][0]);
+    float2* const wC = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(&S.Wc[0][0]) + 1024);
+    if (DIRECT && tid < 64) {
+        const float* w = a.W1 + tid * a.ldW1;
+        wA[tid] = make_float4(w[0], w[1], w[2], w[3]);
+        wC[tid] = make_float2(w[4], a.b1[tid]);
+    }
     if (FIRST) {
+        if (!DIRECT)
         for (int t = tid; t < a.De * 64; t += BG_N * BG_T) Cf[t >> 6][t & 63] = a.W1[(t & 63) * a.ldW1 + a.coff + (t >> 6)];
         for (int t = tid; t < BG_N * 32768 / 16; t += BG_N * BG_T)   // zero-padded raw edge-feature operand tiles
             reinterpret_cast<uint4*>(&S.B1[0][0])[t] = make_uint4(0u, 0u, 0u, 0u);
@@ -265,7 +279,17 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             if (rb < nrows) { ndb = __ldg(a.dst + t0 + rb); nsb = __ldg(a.src + t0 + rb); }
         }
     };
-    gather_ids(0);
+    if (!DIRECT) gather_ids(0);
+    // DIRECT: the row's endpoint ids one tile ahead of their use, so that its input scalars can be requested at the top of the tile
+    int32_t nmy_s = 0, nmy_d = -1;
+    auto row_ids = [&](int i) {
+        nmy_s = 0; nmy_d = -1;
+        if (i < n_mine) {
+            const int32_t t0 = tile_t0(i);
+            if (t0 + row < a.E) { nmy_s = __ldg(a.src + t0 + row); nmy_d = __ldg(a.dst + t0 + row); }
+        }
+    };
+    if (DIRECT) row_ids(0);
     for (int i = 0; i < n_mine; ++i) {
         const int32_t t0 = tile_t0(i);
         const int nrows = min(TILE, a.E - t0);
@@ -280,10 +304,23 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             vv[it] = r < nrows ? __ldg(a.dst + t0 + r) : -1;
         }
         const bool valid = row < nrows;
-        const int32_t my_src = valid ? __ldg(a.src + t0 + row) : 0;
-        const int32_t my_dst = valid ? __ldg(a.dst + t0 + row) : -1;
+        int32_t my_src, my_dst;
+        float2 xi = make_float2(0.f, 0.f), xj = xi;
+        float ee = 0.f;
+        if (DIRECT) {
+            my_src = nmy_s; my_dst = nmy_d;
+            row_ids(i + 1);
+            if (valid) {
+                xi = __ldg(reinterpret_cast<const float2*>(a.x) + my_dst);
+                xj = __ldg(reinterpret_cast<const float2*>(a.x) + my_src);
+                ee = __ldg(a.e_prev + t0 + row);
+            }
+        } else {
+            my_src = valid ? __ldg(a.src + t0 + row) : 0;
+            my_dst = valid ? __ldg(a.dst + t0 + row) : -1;
+        }
         // ---- Pi[dst] + Pj[src] (+ C e in block 1) -> acc (TMEM), 16x256b fragment layout ------------------------------
-        {
+        if (!DIRECT) {
             const int ra = 32 * sp + 16 * half + (lane >> 2), rb = ra + 8;
             const bool va = ra < nrows && !(a.dbg & 2), vb = rb < nrows && !(a.dbg & 2);
             const int32_t da = nda, db = ndb, sa = nsa, sb = nsb;       // fetched one tile ahead
@@ -326,8 +363,8 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
                 }
             }
             tmem_st_16x256b_x8(t_acc + ((uint32_t)(32 * sp + 16 * half) << 16), v);
+            tmem_st_wait();
         }
-        tmem_st_wait();
         BW_TR(1);
         // ---- dm = d e_l + ca[v] + cb[v] e_l (+ arg terms in block 5), kept in registers ---------------------------------
         float4 dm[8];
@@ -428,7 +465,23 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
         BW_TR(7);
         // ---- epilogue 1: hid = relu(acc1) -> B2, relu mask in a register ---------------------------------------------------
         uint32_t hm = 0u;
-        {
+        if (DIRECT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 wa = wA[32 * half + 8 * c + j];
+                    const float2 wc = wC[32 * half + 8 * c + j];
+                    const float pi = fmaf(wa.y, xi.y, fmaf(wa.x, xi.x, wc.y));
+                    const float pj = fmaf(wa.w, xj.y, fmaf(wa.z, xj.x, 0.f));
+                    const float z = valid ? fmaf(ee, wc.x, __fadd_rn(pi, pj)) : 0.f;
+                    y[j] = fmaxf(z, 0.f);
+                    hm |= (z > 0.f ? 1u : 0u) << (8 * c + j);
+                }
+                store_split8<X3>(y, B2h, B2l, row, 4 * half + c);
+            }
+        } else {
             float acc[32];
             tmem_ld32(t_acc + lane_addr + 32 * half, acc);
 #pragma unroll
@@ -607,17 +660,17 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
     if (tid < 32) tmem_dealloc<512>(S.tmem_base);
 }
 
-template <bool FIRST, bool NODE, bool X3>
+template <bool FIRST, bool NODE, bool X3, bool DIRECT = false>
 static int launch_bwd_wg_variant(const CUtensorMap& te, const CUtensorMap& tm, const CUtensorMap& tde, const CUtensorMap& tout,
                                  const CUtensorMap& tdpj, const CUtensorMap& tdpj8, const CUtensorMap& tdpi, const BwdWgArgs& a, int grid,
                                  cudaStream_t st) {
     const int smem = (int)sizeof(BwdWgSmem) + 1024;
     static bool done = false;
     if (!done) {
-        GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GCRL_CUDA(cudaFuncSetAttribute(k_edge_bwd_wg<FIRST, NODE, X3, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    launch_k(k_edge_bwd_wg<FIRST, NODE, X3>, dim3(grid), dim3(BG_N * BG_T), smem, st, te, tm, tde, tout, tdpj, tdpj8, tdpi, a);
+    launch_k(k_edge_bwd_wg<FIRST, NODE, X3, DIRECT>, dim3(grid), dim3(BG_N * BG_T), smem, st, te, tm, tde, tout, tdpj, tdpj8, tdpi, a);
     return GCRL_OK;
 }
 
@@ -628,7 +681,8 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
                        const int32_t* src, const int32_t* dst, int64_t N, int64_t E, const float* m, const float* de,
                        const float* ca, const float* cb, const float* dagg, const int32_t* amin, const int32_t* amax,
                        float* de_prev, float* dPi, float* dPj, float* gW1, float* gW2, float* gb2, cudaStream_t st,
-                       const unsigned char* img_w2, const unsigned char* img_wc) {
+                       const unsigned char* img_w2, const unsigned char* img_wc, const float* x_first, const float* b1,
+                       int Dv) {
     (void)seg_off; (void)b2;
     if (E == 0) return GCRL_OK;
     GCRL_CHECK_ARG(m != nullptr);
@@ -641,6 +695,8 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
     a.img_w2 = img_w2; a.img_wc = img_wc;
+    a.x = x_first; a.b1 = b1;
+    const bool direct = first && b1 != nullptr && first_direct_ok(Dv, De, x_first);
     { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GCRL_WS_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
     CUtensorMap te, tm, tde, tout, tdpj, tdpj8, tdpi;
     int rc;
@@ -656,7 +712,9 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     const int64_t per_cta = (tiles + sm_count() - 1) / sm_count();
     const int64_t grid = (tiles + per_cta - 1) / per_cta;        // every CTA owns >= 1 tile of a contiguous range
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_BWD_FIRST : (no_de ? GCRL_PROF_EDGE_BWD_LAST : GCRL_PROF_EDGE_BWD), st);
-    if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
+    if (direct) rc = x3 ? launch_bwd_wg_variant<true, false, true, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
+                        : launch_bwd_wg_variant<true, false, false, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);
+    else if (first) rc = x3 ? launch_bwd_wg_variant<true, false, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
                        : launch_bwd_wg_variant<true, false, false>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);
     else if (no_de) rc = x3 ? launch_bwd_wg_variant<false, true, true>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st)
                             : launch_bwd_wg_variant<false, true, false>(te, tm, tde, tout, tdpj, tdpj8, tdpi, a, (int)grid, st);

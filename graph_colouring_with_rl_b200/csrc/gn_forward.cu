@@ -413,17 +413,19 @@ int launch_edge_fwd(const BlockW& b, bool first, const float* Pi, const float* P
 int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, const float* Pj, const float* e_prev,
                        const int32_t* seg_off, const int32_t* src, const int32_t* dst, int64_t N, int64_t E,
                        float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax, cudaStream_t st,
-                       const unsigned char* img_w2, const unsigned char* img_wc);
+                       const unsigned char* img_w2, const unsigned char* img_wc, const float* x_first);
+bool first_direct_ok(int Dv, int De, const float* x);
 
 // dispatch on the math mode: tensor-core kernel where its shape constraints hold, else fp32 FFMA
 int launch_edge_fwd_mode(int math_mode, const BlockW& b, bool first, const float* Pi, const float* Pj,
                          const float* e_prev, const int32_t* seg_off, const int32_t* src, const int32_t* dst,
                          int64_t N, int64_t E, float* m_out, float* agg, float* var, int32_t* amin, int32_t* amax,
-                         cudaStream_t st, const unsigned char* img_w2 = nullptr, const unsigned char* img_wc = nullptr) {
+                         cudaStream_t st, const unsigned char* img_w2 = nullptr, const unsigned char* img_wc = nullptr,
+                         const float* x_first = nullptr) {
     const bool tc_ok = first ? (b.De <= 8) : (b.De == 64);
     if (math_mode != GCRL_MATH_FP32 && tc_ok)
         return launch_edge_fwd_wg(b, first, math_mode == GCRL_MATH_BF16X3, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg,
-                                  var, amin, amax, st, img_w2, first ? nullptr : img_wc);
+                                  var, amin, amax, st, img_w2, first ? nullptr : img_wc, first ? x_first : nullptr);
     return launch_edge_fwd(b, first, Pi, Pj, e_prev, seg_off, src, dst, N, E, m_out, agg, var, amin, amax, st);
 }
 
@@ -533,7 +535,10 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         hb[1] = ar.take<float>((size_t)N * 64);
         aggb = ar.take<float>((size_t)N * 256);
     }
-    {
+    // Block 1's projections: not needed when its edge kernel evaluates z1 straight from the raw inputs (DIRECT); a training
+    // pass still writes them into the stash, whose contract (gn_common.cuh) does not depend on the kernel variant
+    const bool first_direct = E > 0 && math_mode != GCRL_MATH_FP32 && first_direct_ok(net.blk[0].Dv, net.blk[0].De, x);
+    if (!first_direct || stash_p) {
         const BlockW& b = net.blk[0];
         int64_t total = N * 64;
         int64_t blocks = (total + 255) / 256;
@@ -556,7 +561,7 @@ int gcrl_gn_forward(const float* params, int vdim, int edim, int gdim, int64_t N
         rc = launch_edge_fwd_mode(math_mode, net.blk[l], l == 0, stash_p ? S.Pi[l] : Pi, stash_p ? S.Pj[l] : Pj, e_prev,
                              seg_off, src, dst, N, E, e_out, agg, stash_p ? S.var[l] : nullptr,
                              stash_p ? S.amin[l] : nullptr, stash_p ? S.amax[l] : nullptr, st,
-                             wimg_tile(wimg, l, WT_W2), wimg_tile(wimg, l, WT_WC));
+                             wimg_tile(wimg, l, WT_W2), wimg_tile(wimg, l, WT_WC), x);
         }
         if (rc) return rc;
         NvtxRange nv_v(last ? "vertex: update MLP + head" : "vertex: update MLP + next projections");
