@@ -130,6 +130,7 @@ struct BwdWgArgs {
     const int32_t* src; const int32_t* dst;
     int32_t N, E;
     const float* ca; const float* cb;
+    const float* m; const float* de;          // e_l and d e_l (the TMA maps' bases; here for the L2 prefetches)
     const float* dagg;
     const int32_t* amin; const int32_t* amax;
     float* dPi; float* dPj;
@@ -303,6 +304,18 @@ __global__ void __launch_bounds__(BG_N * BG_T, 1) k_edge_bwd_wg(const __grid_con
             const int r = (gt >> 4) + 16 * it;
             vv[it] = r < nrows ? __ldg(a.dst + t0 + r) : -1;
         }
+#ifndef GCRL_NO_L2_PREFETCH
+        // Block 1 only: next tile's e_1 / d e_1 rows -> L2 now; their TMA loads are issued as the buffers come free later in
+        // this tile and then land from L2 (4.65 -> 4.23 ms per launch).  Blocks 2-5 measured SLOWER with the same prefetch
+        // (5.58 -> 5.83 ms, block 5 6.48 -> 6.87 ms, and a lower power-capped clock), so they do not issue it.
+        if (FIRST && i + 1 < n_mine) {
+            const int32_t tn = tile_t0(i + 1);
+            const uint32_t nb = (uint32_t)min(TILE, a.E - tn) * 256u;
+            if (gt == 32) l2_prefetch_bulk(a.m + (int64_t)tn * 64, nb);
+            if (!NODE && gt == 160) l2_prefetch_bulk(a.de + (int64_t)tn * 64, nb);
+            if (!FIRST && gt == 224) l2_prefetch_bulk(a.e_prev + (int64_t)tn * 64, nb);
+        }
+#endif
         const bool valid = row < nrows;
         int32_t my_src, my_dst;
         float2 xi = make_float2(0.f, 0.f), xj = xi;
@@ -693,6 +706,7 @@ int launch_edge_bwd_wg(bool first, bool x3, const float* Pi, const float* Pj, co
     a.W1 = W1; a.ldW1 = ldW1; a.coff = coff; a.W2 = W2;
     a.src = src; a.dst = dst; a.N = (int32_t)N; a.E = (int32_t)E;
     a.ca = ca; a.cb = cb; a.dagg = dagg; a.amin = amin; a.amax = amax;
+    a.m = m; a.de = de;
     a.dPi = dPi; a.dPj = dPj; a.gW1 = gW1; a.gW2 = gW2; a.gb2 = gb2;
     a.img_w2 = img_w2; a.img_wc = img_wc;
     a.x = x_first; a.b1 = b1;

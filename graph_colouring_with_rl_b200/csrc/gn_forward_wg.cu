@@ -163,6 +163,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             FW_TR(0);
             dst_s[lt] = nd;
             if (!DIRECT) src_s[lt] = ns;
+#ifdef GCRL_FWD_L2_PREFETCH
+            // Experiment, NOT kept: next tile's e_{l-1} rows -> L2 at the top of this tile, so that the TMA load issued at its
+            // end lands from L2.  Measured 3.50 -> 3.59 ms per launch (and a lower power-capped clock): the landing wait is
+            // 0.5-0.8 k of a 25 k-cycle chain, and the extra requests compete with the other three groups' streams.
+            if (!FIRST && lt == 96 && t0 + TILE < e1)
+                l2_prefetch_bulk(a.e_prev + (int64_t)(t0 + TILE) * 64, (uint32_t)min(TILE, e1 - t0 - TILE) * 256u);
+#endif
             const bool row_ok = nd >= 0;               // DIRECT: this thread's row lies inside the item
             const float2 xi = nxi, xj = nxj;
             const float ee = nee;

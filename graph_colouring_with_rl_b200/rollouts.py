@@ -79,7 +79,9 @@ def greedy_rollouts(graphs, net, record=False, sync_every=8, env=None, graph=Tru
         if graphed is not None and graphed.key != (flat.data_ptr(), net.math_mode, env.x.data_ptr()):
             graphed = env._graphed_step = None
     while steps < max_steps:
-        if steps % sync_every == 0 and bool(env.done.all().item()):
+        # the host looks at `done` every sync_every steps, and before each of the last few: leaf vertices colour themselves,
+        # so the longest episode of a batch usually ends one or two steps short of n (one forward pass of the whole batch each)
+        if (steps % sync_every == 0 or steps + 3 >= max_steps) and bool(env.done.all().item()):
             break
         if graphed is not None:
             a = graphed.replay()
