@@ -383,6 +383,42 @@ def test_gn_backward_tensor_core_modes(weights, math_mode):
                 assert rel <= 0.15, rel
 
 
+@pytest.mark.parametrize('math_mode', [0, 2])
+@pytest.mark.parametrize('dims', [(3, 2), (5, 1), (2, 3)])
+def test_other_input_feature_widths_forward_backward(dims, math_mode):
+    """The library takes any vertex / edge feature width up to 64 (the reference's constructor arguments,
+    architecture.py:102-110), the reference only ever passes (2, 1).  Other widths go through the general block-1 path
+    (projection launch + gather; the straight-from-the-inputs kernels are for (2, 1) only): forward and backward against
+    the oracle on random features over the dataset's graphs."""
+    vd, ed = dims
+    rng = np.random.default_rng(31)
+    params = gn_oracle.init_params(seed=3, vertex_dim=vd, edge_dim=ed)
+    _, x0, ei, ea0, _, _ = batch_of([3, 22, 44, 65], rng)
+    N, E = x0.shape[0], ei.shape[1]
+    torch.manual_seed(5)
+    x = torch.randn(N, vd)
+    ea = torch.randn(E, ed)
+    d_q = torch.randn(N)
+    perm = torch.randperm(E)
+    flat = util.flatten(params).to(DEV)
+    P = ops().pack(ei.to(DEV), N)
+    ea_i = ops().permute_rows(ea.to(DEV), P.perm, True)
+    h, q, st = ops().gn_forward(flat, (vd, ed, 0), P, x.to(DEV), ea_i, with_stash=True, math_mode=math_mode)
+    with torch.no_grad():
+        h_ref, q_ref = gn_oracle.gn_forward(params, x, ei, ea)
+    tol = 2e-6 if math_mode == 0 else 3e-5          # |Q| ~ 0.1 on the default init with unit-variance inputs
+    assert float((q.cpu() - q_ref.view(-1)).abs().max()) <= tol
+    assert float((h.cpu() - h_ref).abs().max()) <= 30 * tol
+    got = ops().gn_backward(flat, (vd, ed, 0), P, x.to(DEV), ea_i, st, d_q=d_q.to(DEV), math_mode=math_mode).cpu().numpy()
+    truth = oracle_grads(params, x, ei, ea, d_q, None, torch.float64)
+    refs = [oracle_grads(params, x, ei, ea, d_q, None, torch.float32),
+            oracle_grads(params, x, ei, ea, d_q, None, torch.float32, perm=perm)]
+    if math_mode == 0:
+        grads_close(got, truth, refs, params)
+    else:
+        grads_close(got, truth, refs, params, rtol=2e-3, noise_amp=128.0)
+
+
 def test_learn_step_vs_reference_golden():
     """TD target, loss, gradients, Adam and the soft update against the unmodified reference's
     DQNAgentGN.learn() (tests/golden/learn_step.npz)."""
