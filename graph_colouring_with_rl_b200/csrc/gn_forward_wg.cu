@@ -65,7 +65,12 @@ struct FwdWgArgs {
 // evaluates it straight from x[dst], x[src] and the edge feature (the operation order of k_node_proj_first + the
 // gather path, bit for bit) and writes relu(z1) into the operand tile: no Pi / Pj rows gathered through L2, no TMEM
 // round trip, no projection launch.  The gather phase was 5.4 k of the 18.7 k cycles of a block-1 tile.
-template <bool FIRST, bool X3, bool ARG, bool DIRECT = false>
+// ATM: the A operands of both products live in TENSOR memory instead of shared memory (tcgen05.mma with A read from
+// TMEM): e_{l-1} goes landing tile -> registers -> bf16 hi | lo columns over the (still unused) accumulator of G2, and
+// relu(z1) is written back IN PLACE over the accumulator columns it was read from, 32 at a time.  Per tile that removes
+// 64 KB of operand writes and ~96 KB of MMA operand reads from shared memory (of ~380 KB), the named barrier of the
+// in-place conversion and the generic->async proxy fences in front of both products.
+template <bool FIRST, bool X3, bool ARG, bool DIRECT = false, bool ATM = false>
 __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_constant__ CUtensorMap tm_in,
                                                               const __grid_constant__ CUtensorMap tm_out, const FwdWgArgs a) {
     pdl_prologue();
@@ -200,6 +205,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 }
                 // ---- hid = relu((A x_i + b1) + B x_j + C e) -> operand tile (thread = row); same operation order as
                 // k_node_proj_first (Pi, Pj) followed by the gather path ((Pi + Pj) + C e) ----------------------------
+                if (ATM) {
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        float y[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float4 wa = wA[32 * half + j];
+                            const float2 wc = wC[32 * half + j];
+                            const float pi = fmaf(wa.y, xi.y, fmaf(wa.x, xi.x, wc.y));
+                            const float pj = fmaf(wa.w, xj.y, fmaf(wa.z, xj.x, 0.f));
+                            const float z = fmaf(ee, wc.x, __fadd_rn(pi, pj));
+                            y[j] = row_ok ? fmaxf(z, 0.f) : 0.f;
+                        }
+                        tmem_st_split32<X3>(t_acc1 + lane_addr + 32 * half, y);
+                    }
+                    tmem_st_wait();
+                } else {
 #pragma unroll 1
                 for (int cb = 0; cb < 8; ++cb) {
                     float y[8];
@@ -213,6 +235,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                         y[j] = row_ok ? fmaxf(z, 0.f) : 0.f;
                     }
                     store_split8<X3>(y, Bh, Bl, lt, cb);
+                }
                 }
                 FW_TR(1);
             } else {
@@ -278,6 +301,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                 mbar_wait_bounded(bar_tma, ph_tma);
                 ph_tma ^= 1;
                 FW_TR(2);
+                if (ATM) {
+                    // thread = tile row: its 64 values -> bf16 hi | lo columns of the G2 accumulator region (dead until G2)
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        float v[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<float4*>(&v[4 * c]) = *reinterpret_cast<const float4*>(l_ptr(M, lt, 8 * half + c));
+                        tmem_st_split32<X3>(t_acc2 + lane_addr + 32 * half, v);
+                    }
+                    tmem_st_wait();
+                } else {
                 float4 x[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -298,15 +333,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                     *reinterpret_cast<uint2*>(T + off) = h;
                     if (X3) *reinterpret_cast<uint2*>(T + 16384 + off) = l;
                 }
+                }
             }
-            fence_proxy_async();
+            if (!ATM) fence_proxy_async();
             tc_fence_before();
             named_sync(bar_id, 128);
             tc_fence_after();
             FW_TR(3);
             if (!FIRST) {
                 if (w == 0 && elect_one()) {
-                    issue_gemm_feat<X3>(t_acc1, smem_u32(Bh), smem_u32(Bl), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
+                    if (ATM) issue_gemm_feat_ts<X3>(t_acc1, t_acc2, smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
+                    else issue_gemm_feat<X3>(t_acc1, smem_u32(Bh), smem_u32(Bl), smem_u32(S.Wc[0]), smem_u32(S.Wc[1]), idesc, true);
                     umma_commit(bar_mma);
                 }
                 mbar_wait_bounded(bar_mma, ph_mma);
@@ -319,6 +356,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
             for (int half = 0; half < 2; ++half) {
                 float acc[32];
                 tmem_ld32(t_acc1 + lane_addr + 32 * half, acc);
+                if (ATM) {
+                    // relu in place: the 32 columns just read take the 16 hi + 16 lo columns of the same K range
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
+                    tmem_st_split32<X3>(t_acc1 + lane_addr + 32 * half, acc);
+                } else {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float y[8];
@@ -326,14 +369,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
                     for (int j = 0; j < 8; ++j) y[j] = fmaxf(acc[8 * c + j], 0.f);
                     store_split8<X3>(y, Bh, Bl, lt, 4 * half + c);
                 }
+                }
             }
+            if (ATM) tmem_st_wait();
             }   // !DIRECT
-            fence_proxy_async();
+            if (!ATM) fence_proxy_async();
             tc_fence_before();
             named_sync(bar_id, 128);
             FW_TR(5);
             if (w == 0 && elect_one()) {
                 tc_fence_after();
+                if (ATM) issue_gemm_feat_ts<X3>(t_acc2, t_acc1, smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);
+                else
                 issue_gemm_feat<X3>(t_acc2, smem_u32(Bh), smem_u32(Bl), smem_u32(S.W2[0]), smem_u32(S.W2[1]), idesc, false);
                 umma_commit(bar_mma);
             }
@@ -415,15 +462,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_edge_fwd_wg(const __grid_cons
     if (tid < 32) tmem_dealloc<512>(S.tmem_base);
 }
 
-template <bool FIRST, bool X3, bool ARG, bool DIRECT = false>
+template <bool FIRST, bool X3, bool ARG, bool DIRECT = false, bool ATM = false>
 static int launch_wg_variant(const CUtensorMap& tin, const CUtensorMap& tout, const FwdWgArgs& a, int grid, cudaStream_t st) {
     const int smem = (int)sizeof(FwdWgSmem) + 1024;
     static bool done = false;
     if (!done) {
-        GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd_wg<FIRST, X3, ARG, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GCRL_CUDA(cudaFuncSetAttribute(k_edge_fwd_wg<FIRST, X3, ARG, DIRECT, ATM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         done = true;
     }
-    launch_k(k_edge_fwd_wg<FIRST, X3, ARG, DIRECT>, dim3(grid), dim3(WG_THREADS), smem, st, tin, tout, a);
+    launch_k(k_edge_fwd_wg<FIRST, X3, ARG, DIRECT, ATM>, dim3(grid), dim3(WG_THREADS), smem, st, tin, tout, a);
     return GCRL_OK;
 }
 
@@ -476,18 +523,22 @@ int launch_edge_fwd_wg(const BlockW& b, bool first, bool x3, const float* Pi, co
     if (grid > (items + WG_N - 1) / WG_N) grid = (items + WG_N - 1) / WG_N;
     const int tok = prof_begin(first ? GCRL_PROF_EDGE_FWD_FIRST : (m_out ? GCRL_PROF_EDGE_FWD : GCRL_PROF_EDGE_FWD_LAST), st);
     const bool want_arg = amin != nullptr;
-#define WG_LAUNCH(F, X, W) rc = launch_wg_variant<F, X, W>(tin, tout, a, (int)grid, st)
+    // A operands in tensor memory (k_edge_fwd_wg<.., ATM>); GCRL_FWD_ATM=0: operand tiles in shared memory (A/B switch)
+    static const bool atm = !(getenv("GCRL_FWD_ATM") && getenv("GCRL_FWD_ATM")[0] == '0');
+#define WG_LAUNCH(F, X, W) rc = atm ? launch_wg_variant<F, X, W, false, true>(tin, tout, a, (int)grid, st) \
+                                    : launch_wg_variant<F, X, W>(tin, tout, a, (int)grid, st)
+#define WG_LAUNCH_D(X, W) rc = atm ? launch_wg_variant<true, X, W, true, true>(tin, tout, a, (int)grid, st) \
+                                   : launch_wg_variant<true, X, W, true>(tin, tout, a, (int)grid, st)
     if (direct) {
-        if (x3) { if (want_arg) rc = launch_wg_variant<true, true, true, true>(tin, tout, a, (int)grid, st);
-                  else rc = launch_wg_variant<true, true, false, true>(tin, tout, a, (int)grid, st); }
-        else    { if (want_arg) rc = launch_wg_variant<true, false, true, true>(tin, tout, a, (int)grid, st);
-                  else rc = launch_wg_variant<true, false, false, true>(tin, tout, a, (int)grid, st); }
+        if (x3) { if (want_arg) WG_LAUNCH_D(true, true); else WG_LAUNCH_D(true, false); }
+        else    { if (want_arg) WG_LAUNCH_D(false, true); else WG_LAUNCH_D(false, false); }
     } else
     if (first) { if (x3) { if (want_arg) WG_LAUNCH(true, true, true); else WG_LAUNCH(true, true, false); }
                  else    { if (want_arg) WG_LAUNCH(true, false, true); else WG_LAUNCH(true, false, false); } }
     else       { if (x3) { if (want_arg) WG_LAUNCH(false, true, true); else WG_LAUNCH(false, true, false); }
                  else    { if (want_arg) WG_LAUNCH(false, false, true); else WG_LAUNCH(false, false, false); } }
 #undef WG_LAUNCH
+#undef WG_LAUNCH_D
     prof_end(tok, st);
     if (rc) return rc;
     GCRL_LAUNCH_CHECK();

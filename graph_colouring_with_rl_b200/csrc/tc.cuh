@@ -203,6 +203,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand read from tensor memory (lane = row, one 32-bit column = two consecutive
+// K elements, the even one in the low half; a K = 16 step is 8 columns)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u) : "memory");
+}
 // arrive on `bar` when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -303,6 +312,43 @@ __device__ __forceinline__ void issue_gemm_rows(uint32_t d_tmem, uint32_t a_hi, 
     } else {
         for (int k = 0; k < rows / 16; ++k) step(k);
     }
+}
+
+// D[128 x 64] (+)= A * B^T with A [128 x 64] in tensor memory as two 32-column halves of 16 hi + 16 lo columns each
+// (half h covers K in [32h, 32h + 32): hi at a_tmem + 32h, lo at a_tmem + 32h + 16 -- the layout an epilogue that converts
+// 32 accumulator columns at a time writes IN PLACE over the columns it has just read), B [64 x 64] K-major in shared memory
+template <bool X3>
+__device__ __forceinline__ void issue_gemm_feat_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                                   bool accumulate_first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t ah = a_tmem + 32 * (k >> 1) + 8 * (k & 1), al = ah + 16;
+        const uint64_t bh = make_desc(b_hi + 32 * k, 16, 1024);
+        umma_bf16_ts(d_tmem, ah, bh, idesc, accumulate_first || k > 0);
+        if (X3) {
+            umma_bf16_ts(d_tmem, al, bh, idesc, true);
+            umma_bf16_ts(d_tmem, ah, make_desc(b_lo + 32 * k, 16, 1024), idesc, true);
+        }
+    }
+}
+// 32 fp32 values of one tile row -> bf16 hi (16 packed columns) | lo (16 packed columns) at taddr (this thread's lane)
+template <bool X3>
+__device__ __forceinline__ void tmem_st_split32(uint32_t taddr, const float v[32]) {
+    uint32_t h[16], l[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (X3) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+        else { h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]); l[j] = 0u; }
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]),
+          "r"(h[8]), "r"(h[9]), "r"(h[10]), "r"(h[11]), "r"(h[12]), "r"(h[13]), "r"(h[14]), "r"(h[15]) : "memory");
+    if (X3)
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+            ::"r"(taddr + 16), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]),
+              "r"(l[8]), "r"(l[9]), "r"(l[10]), "r"(l[11]), "r"(l[12]), "r"(l[13]), "r"(l[14]), "r"(l[15]) : "memory");
 }
 
 // ---- tcgen05.ld: 32 lanes x 32 consecutive 32-bit columns; thread i of the warp gets lane

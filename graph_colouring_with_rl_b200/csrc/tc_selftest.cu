@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
         tc::mbar_init(&S.bar_mma, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc<128>(&S.tmem_base);
+    if (warp == 0) tc::tmem_alloc<256>(&S.tmem_base);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(S.W[0]) + tc::bf_off(o, cb)) = h;
         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(S.W[1]) + tc::bf_off(o, cb)) = l;
     }
-    if (use_tma) {
+    if (use_tma & 1) {
         if (tid == 0) {
             tc::mbar_arrive_expect_tx(&S.bar_tma, 2 * 128 * 64 * 4);
             tc::tma_load_2d(S.L, &tmA, 0, row0, &S.bar_tma);
@@ -124,11 +124,27 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
     }
     convert_tile(S.L, S.A[0], S.A[1], tid, 128);
     convert_tile(S.L2, S.A2[0], S.A2[1], tid, 128);
+    const bool a_in_tmem = (use_tma & 2) != 0;      // D through the A-in-TMEM product (columns [128,192) hold the operand)
+    if (a_in_tmem) {
+        // thread = tile row: its 64 fp32 values -> bf16 hi | lo, 32 columns of K at a time
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(&v[4 * c]) = *reinterpret_cast<const float4*>(tc::l_ptr(S.L, tid, 8 * half + c));
+            tc::tmem_st_split32<true>(tm + ((uint32_t)(32 * warp) << 16) + 128 + 32 * half, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc::tc_fence_before();
+    }
     tc::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
         tc::tc_fence_after();
         // D = A * W^T into columns [0,64)
+        if (a_in_tmem)
+            tc::issue_gemm_feat_ts<true>(tm, tm + 128, tc::smem_u32(S.W[0]), tc::smem_u32(S.W[1]),
+                                         tc::make_idesc_bf16(128, 64, false, false), false);
+        else
         tc::issue_gemm_feat<true>(tm, tc::smem_u32(S.A[0]), tc::smem_u32(S.A[1]), tc::smem_u32(S.W[0]), tc::smem_u32(S.W[1]),
                                   tc::make_idesc_bf16(128, 64, false, false), false);
         // DW = A^T * A2 into columns [64,128): M = 64 (A columns), N = 64 (A2 columns), K = 128 rows
@@ -154,7 +170,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
             }
         }
     }
-    if (do_store && use_tma) {
+    if (do_store && (use_tma & 1)) {
         // TMA store of the (unchanged) fp32 landing tile to rows row0.. of tmOut
         __syncthreads();
         if (tid == 0) {
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(const __grid_constant__ 
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<128>(tm);
+    if (warp == 0) tc::tmem_dealloc<256>(tm);
 }
 
 }  // namespace gcrl

@@ -2,7 +2,8 @@
 run that must pass the same tensor-core parity tests as the default path: the fp32 vertex side under the tensor-core edge
 kernels (GCRL_NODE_IMPL=ffma), the unfused vertex-side launch chains of the forward (GCRL_VERTEX_IMPL=split) and of the
 backward (GCRL_VBWD_IMPL=split), plain launches without programmatic dependent launch (GCRL_PDL=0), and block 1's edge kernels
-through the projection + gather path instead of straight from the raw inputs (GCRL_FIRST_DIRECT=0).
+through the projection + gather path instead of straight from the raw inputs (GCRL_FIRST_DIRECT=0), and the edge forward with its
+MMA A operands as shared-memory tiles instead of tensor-memory columns (GCRL_FWD_ATM=0).
 (Round 1's superseded edge kernels -- single-group and warp-specialised -- were removed in round 2.)"""
 import os
 import subprocess
@@ -15,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize('env', [{'GCRL_NODE_IMPL': 'ffma'}, {'GCRL_VERTEX_IMPL': 'split'}, {'GCRL_VBWD_IMPL': 'split'},
-                                 {'GCRL_PDL': '0'}, {'GCRL_FIRST_DIRECT': '0'}])
+                                 {'GCRL_PDL': '0'}, {'GCRL_FIRST_DIRECT': '0'}, {'GCRL_FWD_ATM': '0'}])
 def test_alternative_implementation_passes_tensor_core_parity(env):
     if os.environ.get('GCRL_ALT_CHILD'):
         pytest.skip('child run')

@@ -40,9 +40,11 @@ def run(rows_total, row0, use_tma, store):
         assert float(out[:row0].abs().max() if row0 else 0) == 0
 
 
-@pytest.mark.parametrize('use_tma', [0, 1])
+@pytest.mark.parametrize('use_tma', [0, 1, 2, 3])
 def test_selftest_full_tile(use_tma):
-    run(300, 37, use_tma, bool(use_tma))
+    """use_tma bit 0: operand tiles brought in by TMA; bit 1: D through the A-in-TMEM product (tcgen05.mma with the A operand
+    read from tensor memory, written there by tcgen05.st in the hi | lo half-tile layout of issue_gemm_feat_ts)."""
+    run(300, 37, use_tma, bool(use_tma & 1))
 
 
 def test_selftest_out_of_bounds_rows_are_zero_filled():
