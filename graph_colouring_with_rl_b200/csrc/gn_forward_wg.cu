@@ -16,6 +16,10 @@
 //   * groups synchronise with named barriers and their own mbarriers only, so one group's MMA / TMA / gather
 //     latency is covered by the other three.
 // TMEM: 128 columns per group (acc1, acc2) = all 512.  Shared memory: 32 + 4 x (32 + 12) + ids = 214 KB.
+// Late round 2 (the default, template parameter ATM): the A operands of both products live in TENSOR memory -- e_{l-1}
+// is split into the columns of acc2 (idle until G2), relu(z1) is written back in place over acc1 -- so T is only the
+// TMA landing tile and the fp32 staging tile of m_l; block 1 with the reference's input widths (DIRECT) evaluates z1
+// from five scalars per edge instead of gathering projections.  DESIGN.md 4.2a / 4.2b.
 #include "gn_common.cuh"
 #include "ws.cuh"
 #include <stdlib.h>
