@@ -15,11 +15,12 @@ Differences that are deliberate and invisible to callers:
     `random.choice`, `np.random.choice`) so seeded runs take the same branches.
 """
 import random
+from collections import OrderedDict
 
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .architecture import GNNetwork
 from .data import Batch
 
@@ -91,6 +92,8 @@ class DQNAgentGN():
         self.episode_no = 0
         self.last_loss = None          # device scalar of the most recent learn() (not in the reference)
         self._node_off1, self._node_off1_n = None, -1
+        self.act_graphs = True         # batch-1 choose_action replays a CUDA graph per (graph, network); False: eager launches
+        self._act_cache = OrderedDict()
 
     # ---- act (dqn_agent.py:108-140) ---------------------------------------------------------------
     def choose_action(self, data, global_features, unassigned_vertices, epsilon=None, test_mode=False):
@@ -107,6 +110,11 @@ class DQNAgentGN():
             net = self.gn_behaviour
             gn_input = data.to(net.device)
             n = gn_input.x.shape[0]
+            if (self.act_graphs and net.dims == (2, 1, 0) and getattr(gn_input, '_unassigned', None) is unassigned_vertices
+                    and gn_input.x.is_cuda):
+                # an observation of this package's environment, scored for the list it was built from: the whole act path
+                # (forward pass + masked first-argmax) replays as one CUDA graph per (graph, network)
+                return self._graphed_act(gn_input, n)
             gf = torch.tensor(global_features, dtype=torch.float).unsqueeze(0).to(net.device)
             with torch.no_grad():
                 _, action_values = net(gn_input, gf, [0] * n, None)
@@ -114,6 +122,55 @@ class DQNAgentGN():
         else:
             vertex_ind = random.choice(unassigned_vertices)
         return vertex_ind
+
+    @torch.no_grad()
+    def _graphed_act(self, data, n):
+        """Batch-1 greedy action (dqn_agent.py:119-134) as ONE CUDA-graph replay: the environment hands out the same static
+        edge tensors for every step of every episode on a graph, so the launch chain of the forward pass (block 1 .. block 5,
+        head) and the masked first-argmax is captured once per (graph, network buffers, math mode) over a private workspace
+        and a static copy of the observation; a call is then one 8 n-byte copy, one graph launch and the `.item()` that returns
+        the Python int (the launch chain walked through Python and ctypes is ~0.25 ms for a 50-vertex graph).  Parameters
+        are read in place from the network's flat buffer, so learning between calls needs no re-capture; a network whose
+        buffer moved (`.to()`, `load_state_dict(assign=True)`) gets a new capture.  At most 64 graphs are kept."""
+        from .architecture import _pack_cache
+        net = self.gn_behaviour
+        flat = net.flat_params()
+        key = (data.edge_index.data_ptr(), n, flat.data_ptr(), net.math_mode)
+        cache = self._act_cache
+        ent = cache.get(key)
+        if ent is not None and ent['edge_index'] is data.edge_index:
+            cache.move_to_end(key)
+            ent['x'].copy_(data.x)
+            ent['graph'].replay()
+            return int(ent['action'].item())
+        dev = flat.device
+        x_s = data.x.float().clone()
+        packed, eattr_i = _pack_cache.get(data.edge_index, n, data.edge_attr.float())
+        node_off = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        ws = torch.empty(lib.gcrl_gn_forward_workspace_bytes(packed.n_vertices, packed.n_edges, 0), dtype=torch.uint8, device=dev)
+
+        def body():
+            _, q, _ = ops.gn_forward(flat, net.dims, packed, x_s, eattr_i, math_mode=net.math_mode, ws=ws)
+            return ops.score_argmax(q, x_s[:, 1].to(torch.int32), node_off)   # -1 = uncoloured (graph_colouring_env.py:124-128)
+        action = body()                                   # eager: the answer of this call, and the warm-up every capture needs
+        out = int(action.item())
+        graph = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            graph.capture_begin()
+            try:
+                action = body()
+            finally:
+                graph.capture_end()
+        cur.wait_stream(side)
+        cache[key] = dict(graph=graph, x=x_s, action=action, ws=ws, packed=packed, eattr=eattr_i, node_off=node_off,
+                          edge_index=data.edge_index)
+        while len(cache) > 64:
+            cache.popitem(last=False)
+        return out
 
     def _masked_argmax(self, q, data, unassigned_vertices, n):
         """np.argmax over q[unassigned_vertices] (dqn_agent.py:131-134) as the device's masked first-argmax.

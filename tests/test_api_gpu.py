@@ -210,6 +210,41 @@ def test_agent_learn_matches_reference_golden():
     assert len(out) == 8 and out[0].x.shape[1] == 2 and out[3].shape == (4, 1)
 
 
+def test_choose_action_cuda_graph_replay_equals_eager_launches():
+    """The batch-1 act path replays one CUDA graph per (graph, network) when the observation comes from this package's
+    environment: same greedy episodes as the eager launch chain, also after the parameters changed IN PLACE between calls
+    (learning), after returning to a graph seen before, and with more graphs than the cache keeps."""
+    from graph_colouring_with_rl_b200 import envs
+    agent = make_agent(trained=True, test_mode=True)
+    targets = [target_of(GRAPHS[g]) for g in (1, 12, 33)]
+    targets.append(targets[0])                                      # back to a graph seen before
+    env = envs.make('graph-colouring-v0', dataset_graphs=targets)
+
+    def episodes():
+        out = []
+        for t in targets:
+            _, cur = env.reset(target=t)
+            seq, done = [], False
+            while not done:
+                data, gf = env.GenerateData_v1(t, cur)
+                a = agent.choose_action(data, gf, cur['unassigned_vertices'], test_mode=True)
+                seq.append(a)
+                cur, _, done, _ = env.step(a)
+            out.append((seq, cur['no_colours_used']))
+        return out
+    agent.act_graphs = False
+    want = episodes()
+    agent.act_graphs = True
+    assert episodes() == want and len(agent._act_cache) == 3        # graph 1 twice: one capture
+    assert episodes() == want                                       # pure replays
+    with torch.no_grad():                                           # "learning": the flat buffer is rewritten in place
+        agent.gn_behaviour.flat_params().mul_(0.7)
+    got = episodes()
+    agent.act_graphs = False
+    assert got == episodes()
+    assert want[0] == want[3]
+
+
 def test_env_dropin_single_graph_traces():
     from graph_colouring_with_rl_b200 import envs
     d = np.load(util.GOLD + '/env_traces.npz')
